@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests (rebuild the seeded inputs behind each golden fixture)."""
+import os
+
+import numpy as np
+import torch
+
+import mintime_b200  # noqa: F401
+from mintime_b200 import synth
+from mintime_b200.spec import default_tsf_config
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# must match oracle/make_golden.py:CASES
+CASES = {
+    "cfg1_b1_f8_id1": (1, 8, [1], False),
+    "b2_f16_id2": (2, 16, [2], True),
+    "b4_f16_mixed": (4, 16, [1, 2, 3, 4], True),
+    "b2_f8_id2": (2, 8, [2, 1], True),
+}
+
+
+def sample_index(numel: int, k: int = 2048) -> torch.Tensor:
+    if numel <= k:
+        return torch.arange(numel)
+    return (torch.arange(k, dtype=torch.float64) * (numel - 1) / (k - 1)).round().long()
+
+
+def sample(t: torch.Tensor, k: int = 2048) -> np.ndarray:
+    flat = t.detach().float().cpu().reshape(-1)
+    return flat[sample_index(flat.numel(), k)].numpy()
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+_CACHE = {}
+
+
+def case_inputs(name):
+    """(cfg, effnet_sd, tsf_sd, meta, frames) for a golden case, rebuilt from the seeds."""
+    if name in _CACHE:
+        return _CACHE[name]
+    B, f, ids, pad = CASES[name]
+    cfg = default_tsf_config(num_frames=f, channels=1280)
+    if "esd" not in _CACHE:
+        _CACHE["esd"] = synth.make_effnet_state_dict(1234)
+    key = ("tsd", f)
+    if key not in _CACHE:
+        _CACHE[key] = synth.make_tsf_state_dict(cfg, 4321)
+    meta = synth.make_batch_meta(B, f, ids, seed=1234, pad_tail=pad)
+    frames = synth.make_frames(B, f, seed=1234, mask=meta["mask"])
+    _CACHE[name] = (cfg, _CACHE["esd"], _CACHE[key], meta, frames)
+    return _CACHE[name]
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
