@@ -1,0 +1,208 @@
+/*
+ * mintime_b200 -- C ABI of libmintime_b200.so (hand-written sm_100a kernels for MINTIME's hot path).
+ *
+ * The reference has no FFI of its own for this path (pure PyTorch): the boundary
+ * a maintainer binds is this header, called from the Python nn.Module shims that keep the reference's
+ * class names / forward signatures (see INTEGRATION.md for the ctypes stubs).  Every entry point
+ *   - takes plain device pointers + sizes + a CUDA stream (cudaStream_t passed as void*),
+ *   - allocates nothing and never synchronises: the caller owns all memory incl. the workspace,
+ *   - is stateless and re-entrant per stream,
+ *   - returns 0 on success, <0 for an invalid argument/shape (mt_last_error() has the text),
+ *     or a positive cudaError_t value if a launch failed.
+ * "T" below is the activation/weight element type selected by `precision`:
+ *   MT_PREC_FP32 -> float (exact path, FFMA kernels), MT_PREC_BF16 -> __nv_bfloat16 (tcgen05 path).
+ *
+ * Each function names the reference code it replaces (paths relative to the reference repo).
+ */
+#ifndef MINTIME_B200_H
+#define MINTIME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_ABI_VERSION 1
+
+enum { MT_PREC_FP32 = 0, MT_PREC_BF16 = 1 };
+enum { MT_OK = 0, MT_ERR_ARG = -1, MT_ERR_WORKSPACE = -2, MT_ERR_UNSUPPORTED = -3, MT_ERR_DRIVER = -4 };
+enum { MT_ATTN_TIME = 0, MT_ATTN_SPACE = 1 };
+enum { MT_IN_F32 = 0, MT_IN_U8 = 1 };
+
+int mt_abi_version(void);
+/* Last error text of the calling thread ("" if none). */
+const char* mt_last_error(void);
+/* 0 if the current CUDA device can run the library (compute capability 10.x), else MT_ERR_UNSUPPORTED. */
+int mt_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed weights (device pointers).  Packing (BatchNorm folding, layout, dtype) is done once at load
+ * time by the host shim (weights.py); layouts:
+ *   pointwise conv / linear  : w  T [Cout][Cin]   (BN scale folded into rows), shift f32 [Cout]
+ *   depthwise conv           : w  f32 [k*k][C]    (BN scale folded),            shift f32 [C]
+ *   stem conv                : w  f32 [27][32]    ((ky*3+kx)*3+ci major, BN scale folded), shift f32 [32]
+ *   squeeze-excite           : f32, reduce [Sq][C] + bias [Sq], expand [C][Sq] + bias [C]
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* w;      /* T   [cout][cin] */
+  const float* shift; /* f32 [cout] (BN beta - mean*scale, or the linear bias); may be NULL */
+} mt_pw_t;
+
+typedef struct {
+  mt_pw_t expand;          /* w == NULL when expand_ratio == 1 (block 0)   model.py:57-64   */
+  const float* dw_w;       /* [k*k][cexp]                                   model.py:66-73   */
+  const float* dw_shift;   /* [cexp] */
+  const float* se_reduce_w; /* [sq][cexp]                                   model.py:76-80   */
+  const float* se_reduce_b; /* [sq] */
+  const float* se_expand_w; /* [cexp][sq] */
+  const float* se_expand_b; /* [cexp] */
+  mt_pw_t project;         /* [cout][cexp]                                  model.py:83-86   */
+} mt_mbconv_t;
+
+typedef struct {
+  const float* stem_w;     /* model.py:160-165 */
+  const float* stem_shift;
+  mt_mbconv_t blocks[16];
+  mt_pw_t head;            /* model.py:193-197 */
+} mt_effnet_b0_weights_t;
+
+typedef struct {
+  const float* ln_g; const float* ln_b;    /* PreNorm LayerNorm            size_invariant_timesformer.py:18-26 */
+  const void* w_qkv;                       /* T [3*inner][dim], q rows pre-scaled by dim_head^-0.5 (:114) */
+  const void* w_out; const float* b_out;   /* T [dim][inner], f32 [dim]                                   (:103-106) */
+} mt_attn_weights_t;
+
+typedef struct {
+  const float* ln_g; const float* ln_b;
+  const void* w1; const float* b1;         /* T [8*dim][dim] rows interleaved in blocks of 32 (x | gate), f32 [8*dim] same order (:68-73) */
+  const void* w2; const float* b2;         /* T [dim][4*dim], f32 [dim] */
+} mt_ff_weights_t;
+
+typedef struct {
+  int dim, depth, heads, dim_head, num_frames, num_patches, channels, num_classes;
+  int enable_pos_emb, enable_size_emb;
+} mt_tsf_cfg_t;
+
+#define MT_TSF_MAX_DEPTH 16
+typedef struct {
+  const void* w_patch; const float* b_patch;   /* T [dim][channels], f32 [dim]   (:175) */
+  const float* cls_token;                      /* f32 [dim]                      (:176) */
+  const float* pos_emb;                        /* f32 [num_frames*channels+1][dim] (:178) */
+  const float* size_emb;                       /* f32 same shape or NULL          (:179-180) */
+  mt_attn_weights_t time_attn[MT_TSF_MAX_DEPTH];
+  mt_attn_weights_t space_attn[MT_TSF_MAX_DEPTH];
+  mt_ff_weights_t ff[MT_TSF_MAX_DEPTH];
+  const float* out_ln_g; const float* out_ln_b; /* to_out.0 (:195-198) */
+  const float* out_w; const float* out_b;       /* f32 [num_classes][dim], [num_classes] */
+} mt_tsf_weights_t;
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-model entry points
+ * ------------------------------------------------------------------------------------------- */
+
+/* EfficientNet.forward (models/efficientnet/efficientnet_pytorch/model.py:267-288), eval mode.
+ *   x      : frames, NHWC [n_img][224][224][3], f32 (MT_IN_F32) or u8 (MT_IN_U8), raw 0..255
+ *   feats  : T [n_img*49][1280]  == NHWC feature map == the 'b (f h w) c' token layout of
+ *            size_invariant_timesformer.py:227, i.e. the reference's (n_img,1280,7,7) output permuted.
+ * Workspace: mt_effnet_b0_workspace_bytes(n_img, precision). */
+size_t mt_effnet_b0_workspace_bytes(int n_img, int precision);
+int mt_effnet_b0_fwd(const mt_effnet_b0_weights_t* w, const void* x, int x_dtype, void* feats, int n_img,
+                     int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SizeInvariantTimeSformer.forward (models/size_invariant_timesformer.py:224-276).
+ *   feats          : T [B][f*49][channels]
+ *   mask           : u8 [B][f]           (bool)       identities_mask : u8 [B][f][f]
+ *   size_embedding : i32 [B][f]                        positions       : i64 [B][1+f*49]
+ *   logits         : f32 [B][num_classes]
+ *   space_attn/time_attn : f32 [B*heads][1+f*49] each (last layer's CLS attention, (b h) row order,
+ *                    :271) or NULL when attention maps are not required. */
+size_t mt_tsf_workspace_bytes(const mt_tsf_cfg_t* cfg, int batch, int precision);
+int mt_tsf_fwd(const mt_tsf_weights_t* w, const mt_tsf_cfg_t* cfg, const void* feats, const uint8_t* mask,
+               const uint8_t* identities_mask, const int32_t* size_embedding, const int64_t* positions,
+               float* logits, float* space_attn, float* time_attn, int batch, int precision, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Building blocks (the whole-model calls are sequences of these; exported for per-kernel parity
+ * tests and for callers that fuse differently)
+ * ------------------------------------------------------------------------------------------- */
+
+/* 1x1 conv / linear:  out[m][n] = act( sum_k a[m][k]*gate[m/rows_per_gate][k] * w[n][k] + shift[n] ) + residual[m][n]
+ * Replaces F.conv2d 1x1 + BatchNorm2d(eval) + swish (+ SE scale on the input, + skip add):
+ * model.py:100-103 (expand), :113-119 (SE multiply + project + bn2), :122-127 (skip), :286 (head);
+ * and nn.Linear (to_qkv, size_invariant_timesformer.py:111).
+ * gate (f32 [m/rows_per_gate][k]) and residual (T [m][n]) may be NULL; act: 0 none, 1 swish. */
+int mt_pointwise_fwd(int precision, const void* a, const void* w, const float* shift, const float* gate,
+                     int rows_per_gate, const void* residual, int act, void* out, int m, int n, int k, void* stream);
+
+/* x[m][n] += sum_k a[m][k]*w[n][k] + bias[n]   (x: f32 residual stream, in place)
+ * Replaces to_out Linear + residual add (size_invariant_timesformer.py:144,265,267) and FF net.3 + residual (:73,268). */
+int mt_linear_residual_fwd(int precision, const void* a, const void* w, const float* bias, float* x, int m, int n,
+                           int k, void* stream);
+
+/* GEGLU feed-forward first half: out[m][j] = u[j] * gelu_erf(g[j]),  (u|g) = a*W1^T + b1   (:60-63, :68-70)
+ * w/bias rows are interleaved in blocks of 32 (32 u-rows, then their 32 gate rows); n = 2*n_out. */
+int mt_linear_geglu_fwd(int precision, const void* a, const void* w, const float* bias, void* out, int m, int n,
+                        int k, void* stream);
+
+/* Token build (:225-248): x[b][0] = cls + pos[positions[b][0]] + size[0];
+ * x[b][1+t] = feats[b][t]*Wp^T + bp + pos[positions[b][1+t]] + size[size_embedding[b][t/49]]   (x: f32 [B][1+f*49][dim]) */
+int mt_patch_embed_fwd(int precision, const mt_tsf_weights_t* w, const mt_tsf_cfg_t* cfg, const void* feats,
+                       const int32_t* size_embedding, const int64_t* positions, float* x, int batch, void* stream);
+
+/* nn.LayerNorm(dim) over the last axis, eps 1e-5 (:18-26): f32 [rows][dim] -> T [rows][dim] */
+int mt_layernorm_fwd(int precision, const float* x, const float* gamma, const float* beta, void* out, int rows,
+                     int dim, void* stream);
+
+/* Attention core of Attention.forward (:114-141) on an already projected qkv (q pre-scaled):
+ *   qkv T [B][1+f*n][3*heads*dim_head] -> out T [B][1+f*n][heads*dim_head] (heads merged, before to_out)
+ *   mode MT_ATTN_TIME : groups (b,h,patch): frames attend frames (+CLS key), bias = mask[b][k] & identities_mask[b][q][k]
+ *   mode MT_ATTN_SPACE: groups (b,h,frame): patches attend patches (+CLS key), no mask
+ *   CLS row: attends all tokens with the padded-frame mask; cls_attn f32 [B*heads][1+f*n] (may be NULL). */
+int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t* mask, const uint8_t* identities_mask,
+                        int mode, void* out, float* cls_attn, int batch, int f, int n, int heads, int dim_head,
+                        void* stream);
+
+/* Stem: ZeroPad2d(0,1,0,1) + conv 3x3 s2 (3->32) + BN + swish (utils.py:248-276, model.py:276)
+ *   x NHWC [n_img][H][W][3] (f32/u8) -> out T NHWC [n_img][H/2][W/2][32] */
+int mt_stem_fwd(int precision, const void* x, int x_dtype, const float* w, const float* shift, void* out, int n_img,
+                int h, int w_, void* stream);
+
+/* Depthwise kxk stride s conv with TF-SAME padding + BN + swish, plus the SE squeeze sums
+ * (model.py:105-107,110): in T NHWC [n_img][h][w][c] -> out T NHWC [n_img][ceil(h/s)][ceil(w/s)][c];
+ * pool_sum f32 [n_img][c] must be zeroed by the caller and receives sum over pixels of out. */
+int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_sum,
+                  int n_img, int h, int w_, int c, int k, int s, void* stream);
+
+/* SE excitation (model.py:111-115): gate[i][c] = sigmoid(We*swish(Wr*(pool_sum[i]/hw) + br) + be) */
+int mt_se_gate_fwd(const float* pool_sum, int hw, const float* wr, const float* br, const float* we, const float* be,
+                   float* gate, int n_img, int c, int sq, void* stream);
+
+/* Classification head (:195-198,270-276): logits[b] = LayerNorm(x[b][0]) * W^T + bias */
+int mt_head_fwd(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* bias, float* logits,
+                int batch, int tokens, int dim, int num_classes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Diagnostics (used by bench.py; off by default, no effect on results)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  char name[64];        /* kernel class, e.g. "gemm_tc geglu N4096 K512" */
+  double ms_total;      /* CUDA-event time summed over `count` launches */
+  double flops_total;   /* algorithmic flops of those launches */
+  double bytes_total;   /* algorithmic HBM bytes of those launches */
+  int count;
+} mt_prof_entry_t;
+/* While enabled, every kernel launch is bracketed by CUDA events on its stream. */
+void mt_prof_enable(int on);
+void mt_prof_reset(void);
+/* Waits for the recorded events; writes per-name aggregates sorted by time; returns #names. */
+int mt_prof_collect(mt_prof_entry_t* out, int max_entries);
+/* Kernels launched by this library in this process so far. */
+unsigned long long mt_prof_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINTIME_B200_H */

@@ -1,0 +1,194 @@
+// Internal declarations shared by the kernels behind include/mintime_b200.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mintime_b200.h"
+
+namespace mt {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ host-side error reporting
+void set_error(const char* fmt, ...);
+int cuda_status(cudaError_t e, const char* what);
+
+#define MT_REQUIRE(cond, ...)     \
+  do {                            \
+    if (!(cond)) {                \
+      mt::set_error(__VA_ARGS__); \
+      return MT_ERR_ARG;          \
+    }                             \
+  } while (0)
+
+// ------------------------------------------------------------------ diagnostics (mt_prof_* in the C ABI)
+void count_launch();
+// When profiling is enabled, brackets the launches issued in its scope with CUDA events on `stream`
+// and books the elapsed time under `name` with the algorithmic flops / bytes of that launch.
+struct ProfScope {
+  ProfScope(cudaStream_t stream, double flops, double bytes, const char* fmt, ...);
+  ~ProfScope();
+  int slot;
+  cudaStream_t st;
+};
+
+#define MT_LAUNCH_CHECK(what)                                   \
+  do {                                                          \
+    cudaError_t e__ = cudaGetLastError();                       \
+    if (e__ != cudaSuccess) return mt::cuda_status(e__, what);  \
+    mt::count_launch();                                         \
+  } while (0)
+
+// ------------------------------------------------------------------ element helpers
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// swish / SiLU: x * sigmoid(x)  (reference utils.py:66-69).  The exact path uses expf, the bf16 path
+// the fast intrinsic (its error is far below bf16 resolution).
+template <bool kExact>
+__device__ __forceinline__ float silu(float x) {
+  if (kExact) return x / (1.0f + expf(-x));
+  return __fdividef(x, 1.0f + __expf(-x));
+}
+template <bool kExact>
+__device__ __forceinline__ float sigmoidf_(float x) {
+  if (kExact) return 1.0f / (1.0f + expf(-x));
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+// F.gelu default (erf form), size_invariant_timesformer.py:63
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// 8 consecutive elements <-> registers
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------ GEMM epilogues
+enum EpiKind { EPI_STORE = 0, EPI_RESID_F32 = 1, EPI_GEGLU = 2, EPI_PATCH_EMBED = 3 };
+
+struct EpiParams {
+  int kind;
+  int M, N;            // GEMM extents (N counts weight rows, i.e. 2x the output width for GEGLU)
+  const float* bias;   // [N] or null
+  int act;             // EPI_STORE: 0 none, 1 swish
+  const void* resid;   // EPI_STORE: T [M][ldo] or null (added after act)
+  void* out;           // T* (STORE, GEGLU) or float* (RESID_F32, PATCH_EMBED)
+  int ldo;             // output row stride (elements)
+  // EPI_PATCH_EMBED
+  int rows_per_batch;  // f * n
+  int n_patches;       // n
+  int frames;          // f
+  const float* pos_tab;
+  const float* size_tab;
+  const long long* positions;  // [B][rows_per_batch + 1] or null (-> arange)
+  const int* size_idx;         // [B][f]
+};
+
+struct GemmArgs {
+  const void* a;   // T [M][K]
+  const void* w;   // T [N][K]
+  int M, N, K;
+  const float* gate;  // f32 [M / rows_per_gate][K] or null
+  int rows_per_gate;
+  EpiParams epi;
+};
+
+// One group of 8 consecutive output columns [col, col+8) of row `row` (both already bounds-checked).
+template <typename T, int KIND>
+__device__ __forceinline__ void epi_store8(const EpiParams& p, int row, int col, float (&v)[8]) {
+  constexpr bool kExact = sizeof(T) == 4;
+  if (p.bias) {
+    float b[8];
+    load8(p.bias + col, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += b[i];
+  }
+  if (KIND == EPI_STORE) {
+    if (p.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = silu<kExact>(v[i]);
+    }
+    const size_t off = (size_t)row * p.ldo + col;
+    if (p.resid) {
+      float r[8];
+      load8(reinterpret_cast<const T*>(p.resid) + off, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += r[i];
+    }
+    store8(reinterpret_cast<T*>(p.out) + off, v);
+  } else if (KIND == EPI_RESID_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
+    float r[8];
+    load8(o, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+    store8(o, v);
+  } else if (KIND == EPI_PATCH_EMBED) {
+    const int b = row / p.rows_per_batch, t = row - b * p.rows_per_batch;
+    const size_t orow = (size_t)row + b + 1;
+    const long long pos = p.positions ? p.positions[(size_t)b * (p.rows_per_batch + 1) + 1 + t] : (long long)(1 + t);
+    float e[8];
+    load8(p.pos_tab + (size_t)pos * p.ldo + col, e);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += e[i];
+    if (p.size_tab) {
+      const int si = p.size_idx[b * p.frames + t / p.n_patches];
+      load8(p.size_tab + (size_t)si * p.ldo + col, e);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += e[i];
+    }
+    store8(reinterpret_cast<float*>(p.out) + orow * p.ldo + col, v);
+  }
+}
+
+// GEGLU: u = 8 packed columns [col, col+8), g = their gate columns [col+32, col+40) of the same
+// 64-wide interleave block; writes out[row][ (col/64)*32 + col%64 .. +8 ).
+template <typename T>
+__device__ __forceinline__ void epi_geglu8(const EpiParams& p, int row, int col, float (&u)[8], float (&g)[8]) {
+  if (p.bias) {
+    float b[8];
+    load8(p.bias + col, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] += b[i];
+    load8(p.bias + col + 32, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += b[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] *= gelu_erf(g[i]);
+  const int ocol = (col >> 6) * 32 + (col & 63);
+  store8(reinterpret_cast<T*>(p.out) + (size_t)row * p.ldo + ocol, u);
+}
+
+// ------------------------------------------------------------------ internal launchers
+int launch_gemm(int precision, const GemmArgs& g, cudaStream_t stream);
+
+}  // namespace mt

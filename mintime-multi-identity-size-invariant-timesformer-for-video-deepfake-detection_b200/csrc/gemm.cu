@@ -1,0 +1,503 @@
+// out = epilogue(A[M][K] * W[N][K]^T): the contraction behind every 1x1 convolution of EfficientNet-B0
+// (reference model.py:101,118,286 via utils.py:273-276) and every nn.Linear of the TimeSformer
+// (size_invariant_timesformer.py:68-73,102-106,175).
+//
+//  * gemm_tc_kernel   (bf16): TMA-staged 128 x block_n x 64 tiles (128-byte swizzle), tcgen05.mma with
+//    fp32 accumulators in TMEM (double buffered), warp-specialised: 1 TMA producer warp, 1 MMA issuer
+//    warp, 4 epilogue warps (tcgen05.ld -> fused epilogue -> global), + 4 "gate" warps when the A
+//    operand carries the squeeze-excite scale.  Persistent over output tiles.
+//  * gemm_simt_kernel (fp32 / any T): plain FFMA tiles with the same epilogues -- the exact path.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mt {
+
+// =====================================================================================================
+// tcgen05 kernel
+// =====================================================================================================
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // 64 bf16 = one 128-byte swizzle row
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxStages = 8;
+
+struct TcParams {
+  int M, N, K;
+  int block_n;      // multiple of 16, <= 256 (multiple of 64 for GEGLU)
+  int stages;
+  int tiles_m, tiles_n;
+  int tmem_cols;    // power of two >= 2 * block_n
+  const float* gate;
+  int rows_per_gate;
+  EpiParams epi;
+};
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int stages) {
+    if (++stage == stages) { stage = 0; phase ^= 1; }
+  }
+};
+
+template <typename T, int KIND, bool GATED>
+__global__ void __launch_bounds__(GATED ? 320 : 192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up: [A stages][B stages][barriers][tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage_bytes = p.block_n * kBlockK * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.stages * kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* gated_bar = bars + 2 * kMaxStages;
+  uint64_t* tmem_full = bars + 3 * kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&gated_bar[s], 128);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      PipeState ps;
+      const uint32_t tx_bytes = (uint32_t)(kAStageBytes + b_stage_bytes);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * kBlockM;
+        const int n0 = (tile % p.tiles_n) * p.block_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+          ptx::tma_load_2d(smem_a + ps.stage * kAStageBytes, &tmap_a, &full_bar[ps.stage], kb * kBlockK, m0);
+          ptx::tma_load_2d(smem_b + ps.stage * b_stage_bytes, &tmap_b, &full_bar[ps.stage], kb * kBlockK, n0);
+          ps.advance(p.stages);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      PipeState ps;
+      const uint32_t idesc = ptx::umma_idesc_bf16_f32(kBlockM, (uint32_t)p.block_n);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(GATED ? &gated_bar[ps.stage] : &full_bar[ps.stage], ps.phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem_a + ps.stage * kAStageBytes);
+          const uint32_t b_addr = ptx::smem_u32(smem_b + ps.stage * b_stage_bytes);
+          const int k_left = p.K - kb * kBlockK;
+          const int ksteps = k_left >= kBlockK ? 4 : (k_left + 15) / 16;  // TMA zero-filled the K tail
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * 32);
+            const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * 32);
+            ptx::umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[ps.stage]);  // smem slot free once these MMAs retire
+          ps.advance(p.stages);
+        }
+        ptx::umma_commit(&tmem_full[as]);          // accumulator ready for the epilogue warps
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ===================================================================== epilogue (4 warps)
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / p.tiles_n) * kBlockM;
+      const int n0 = (tile % p.tiles_n) * p.block_n;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      ptx::mbar_wait(&tmem_full[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
+      if (KIND == EPI_GEGLU) {
+        for (int c = 0; c < p.block_n; c += 64) {
+          uint32_t ru[32], rg[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c, ru);
+          ptx::tmem_ld_32x32b_x32(taddr + c + 32, rg);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = n0 + c + g * 8;
+              if (col < p.N) {
+                float u[8], gg[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { u[i] = __uint_as_float(ru[g * 8 + i]); gg[i] = __uint_as_float(rg[g * 8 + i]); }
+                epi_geglu8<T>(p.epi, row, col, u, gg);
+              }
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < p.block_n; c += 32) {
+          if (p.block_n - c >= 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + c, r);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = n0 + c + g * 8;
+                if (col < p.N) {
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                  epi_store8<T, KIND>(p.epi, row, col, v);
+                }
+              }
+            }
+          } else {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(taddr + c, r);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const int col = n0 + c + g * 8;
+                if (col < p.N) {
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                  epi_store8<T, KIND>(p.epi, row, col, v);
+                }
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[as]);
+    }
+  } else if (GATED) {
+    // ===================================================================== SE-gate warps (4 warps)
+    // Multiply the freshly landed A tile by gate[image(row)][k] in shared memory (reference
+    // model.py:115: x = sigmoid(se) * x, ahead of the project conv), then hand it to the MMA warp.
+    const int r = threadIdx.x - 192;  // tile row 0..127
+    PipeState ps;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * kBlockM;
+      const int row = m0 + r;
+      const float* grow = p.gate + (size_t)((row < p.M ? row : p.M - 1) / p.rows_per_gate) * p.K;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
+        uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int k = kb * kBlockK + c * 8;
+          if (k < p.K) {
+            uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
+            uint4 u = *ptr;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            const float4 g0 = *reinterpret_cast<const float4*>(grow + k);
+            const float4 g1 = *reinterpret_cast<const float4*>(grow + k + 4);
+            float2 f;
+            f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
+            f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
+            f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
+            f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
+            *ptr = u;
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&gated_bar[ps.stage]);
+        ps.advance(p.stages);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// =====================================================================================================
+// SIMT kernel (exact path): 64x64 tile, 256 threads, 4 rows x (2+2) columns per thread so that a
+// GEGLU u-column and its gate column (+32) live in the same thread.
+// =====================================================================================================
+template <typename T, int KIND, bool GATED>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const T* A = reinterpret_cast<const T*>(g.a);
+  const T* W = reinterpret_cast<const T*>(g.w);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    for (int e = threadIdx.x; e < BM * BK; e += 256) {
+      const int r = e / BK, kk = e % BK;
+      const int row = m0 + r, k = k0 + kk;
+      float v = 0.f;
+      if (row < g.M && k < g.K) {
+        v = to_f(A[(size_t)row * g.K + k]);
+        if (GATED) v *= g.gate[(size_t)(row / g.rows_per_gate) * g.K + k];
+      }
+      As[kk][r] = v;
+      const int col = n0 + r;
+      Bs[kk][r] = (col < g.N && k < g.K) ? to_f(W[(size_t)col * g.K + k]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      b[0] = Bs[kk][tx * 2]; b[1] = Bs[kk][tx * 2 + 1]; b[2] = Bs[kk][32 + tx * 2]; b[3] = Bs[kk][33 + tx * 2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  constexpr bool kExact = sizeof(T) == 4;
+  const EpiParams& p = g.epi;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= g.M) continue;
+    if (KIND == EPI_GEGLU) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = n0 + tx * 2 + j;  // u column; gate at +32
+        if (col < g.N) {
+          float u = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
+          float gt = acc[i][j + 2] + (p.bias ? p.bias[col + 32] : 0.f);
+          const int ocol = (col >> 6) * 32 + (col & 63);
+          reinterpret_cast<T*>(p.out)[(size_t)row * p.ldo + ocol] = from_f<T>(u * gelu_erf(gt));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = n0 + tx * 2 + (j & 1) + (j >> 1) * 32;
+        if (col >= g.N) continue;
+        float v = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
+        if (KIND == EPI_STORE) {
+          if (p.act == 1) v = silu<kExact>(v);
+          const size_t off = (size_t)row * p.ldo + col;
+          if (p.resid) v += to_f(reinterpret_cast<const T*>(p.resid)[off]);
+          reinterpret_cast<T*>(p.out)[off] = from_f<T>(v);
+        } else if (KIND == EPI_RESID_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col;
+          *o = *o + v;
+        } else if (KIND == EPI_PATCH_EMBED) {
+          const int b = row / p.rows_per_batch, t = row - b * p.rows_per_batch;
+          const size_t orow = (size_t)row + b + 1;
+          const long long pos = p.positions ? p.positions[(size_t)b * (p.rows_per_batch + 1) + 1 + t] : (long long)(1 + t);
+          v += p.pos_tab[(size_t)pos * p.ldo + col];
+          if (p.size_tab) v += p.size_tab[(size_t)p.size_idx[b * p.frames + t / p.n_patches] * p.ldo + col];
+          reinterpret_cast<float*>(p.out)[orow * p.ldo + col] = v;
+        }
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// 2D bf16 row-major [rows][cols] tensor, box = [box_rows][64 cols], 128-byte swizzle, zero OOB fill.
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+  auto enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MT_ERR_DRIVER;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box_rows=%d base=%p", (int)r, rows, cols, box_rows, base);
+    return MT_ERR_DRIVER;
+  }
+  return MT_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int KIND, bool GATED>
+int launch_tc(const GemmArgs& g, cudaStream_t stream) {
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.gate = g.gate; p.rows_per_gate = g.rows_per_gate;
+  p.epi = g.epi;
+  // tile width: whole N if it fits one UMMA (<= 256), else 256 / 128 so that the tile count divides well
+  int bn;
+  if (KIND == EPI_GEGLU) {
+    bn = 256;
+  } else {
+    const int parts = (g.N + 255) / 256;            // fewest UMMA-wide (<= 256) column tiles ...
+    bn = ((g.N + parts - 1) / parts + 15) / 16 * 16;  // ... of equal width (multiple of 16)
+  }
+  p.block_n = bn;
+  p.tiles_m = (g.M + kBlockM - 1) / kBlockM;
+  p.tiles_n = (g.N + bn - 1) / bn;
+  int tmem = 32;
+  while (tmem < 2 * bn) tmem <<= 1;
+  p.tmem_cols = tmem;
+  const int stage_bytes = kAStageBytes + bn * kBlockK * 2;
+  const int budget = (bn <= 128 ? 100 : 200) * 1024;   // <=128-wide tiles: leave room for 2 CTAs / SM
+  int stages = budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (3 * kMaxStages + 4) * 8 + 16;
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, g.a, g.M, g.K, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, g.w, g.N, g.K, bn);
+  if (rc) return rc;
+
+  auto kern = gemm_tc_kernel<bf16, KIND, GATED>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc)");
+    attr_set = true;
+  }
+  const int ctas_per_sm = bn <= 128 ? 2 : 1;
+  int grid = p.tiles_m * p.tiles_n;
+  if (grid > num_sms() * ctas_per_sm) grid = num_sms() * ctas_per_sm;
+  kern<<<grid, GATED ? 320 : 192, smem, stream>>>(ta, tb, p);
+  MT_LAUNCH_CHECK("gemm_tc_kernel");
+  return MT_OK;
+}
+
+template <typename T, int KIND, bool GATED>
+int launch_simt(const GemmArgs& g, cudaStream_t stream) {
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+  gemm_simt_kernel<T, KIND, GATED><<<grid, 256, 0, stream>>>(g);
+  MT_LAUNCH_CHECK("gemm_simt_kernel");
+  return MT_OK;
+}
+
+template <int KIND, bool GATED>
+int dispatch_prec(int precision, const GemmArgs& g, cudaStream_t stream) {
+  if (precision == MT_PREC_BF16) return launch_tc<KIND, GATED>(g, stream);
+  if (precision == MT_PREC_FP32) return launch_simt<float, KIND, GATED>(g, stream);
+  if (precision == 2) return launch_simt<bf16, KIND, GATED>(g, stream);  // debug: bf16 storage, FFMA math
+  set_error("unknown precision %d", precision);
+  return MT_ERR_ARG;
+}
+
+}  // namespace
+
+int launch_gemm(int precision, const GemmArgs& g, cudaStream_t stream) {
+  MT_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  MT_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "gemm: N (%d) and K (%d) must be multiples of 8", g.N, g.K);
+  MT_REQUIRE(g.a && g.w && g.epi.out, "gemm: null operand");
+  const bool gated = g.gate != nullptr;
+  MT_REQUIRE(!gated || g.rows_per_gate > 0, "gemm: rows_per_gate must be > 0 with a gate");
+  static const char* kKind[] = {"store", "resid", "geglu", "embed"};
+  const double es = precision == MT_PREC_FP32 ? 4.0 : 2.0;
+  const double mn = (double)g.M * g.N;
+  double bytes = ((double)g.M * g.K + (double)g.N * g.K) * es;
+  if (g.epi.kind == EPI_STORE) bytes += mn * es * (g.epi.resid ? 2 : 1);
+  else if (g.epi.kind == EPI_RESID_F32) bytes += mn * 8;
+  else if (g.epi.kind == EPI_GEGLU) bytes += mn / 2 * es;
+  else if (g.epi.kind == EPI_PATCH_EMBED) bytes += mn * 4 * (g.epi.size_tab ? 3 : 2);
+  ProfScope prof(stream, 2.0 * mn * g.K, bytes, "gemm_%s %s%s N%d K%d", precision == MT_PREC_BF16 ? "tc" : "simt",
+                 (g.epi.kind >= 0 && g.epi.kind < 4) ? kKind[g.epi.kind] : "?", gated ? "+gate" : "", g.N, g.K);
+  switch (g.epi.kind) {
+    case EPI_STORE:
+      return gated ? dispatch_prec<EPI_STORE, true>(precision, g, stream)
+                   : dispatch_prec<EPI_STORE, false>(precision, g, stream);
+    case EPI_RESID_F32:
+      MT_REQUIRE(!gated, "gemm: gate unsupported for this epilogue");
+      return dispatch_prec<EPI_RESID_F32, false>(precision, g, stream);
+    case EPI_GEGLU:
+      MT_REQUIRE(!gated && g.N % 64 == 0, "gemm: GEGLU needs N %% 64 == 0 (N=%d)", g.N);
+      return dispatch_prec<EPI_GEGLU, false>(precision, g, stream);
+    case EPI_PATCH_EMBED:
+      MT_REQUIRE(!gated, "gemm: gate unsupported for this epilogue");
+      return dispatch_prec<EPI_PATCH_EMBED, false>(precision, g, stream);
+  }
+  set_error("gemm: unknown epilogue %d", g.epi.kind);
+  return MT_ERR_ARG;
+}
+
+}  // namespace mt

@@ -1,0 +1,467 @@
+// Size-Invariant TimeSformer forward (reference models/size_invariant_timesformer.py:224-276).
+// Linear layers run in gemm.cu; this file holds LayerNorm, the divided (time / space) attention core
+// with the identity mask, the CLS-row attention, token assembly for the CLS row, the head, and the
+// layer schedule.  Residual stream x is fp32 [B][1+f*n][dim]; GEMM operands are T.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace mt {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm(dim, eps 1e-5) f32 -> T, one warp per row  (PreNorm, :18-26)
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                        const float* __restrict__ b, T* __restrict__ out, int rows,
+                                                        int dim) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = dim >> 7;  // float4 per lane
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * dim);
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      v[i] = xr[i * 32 + lane];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  const float mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)dim + 1e-5f);
+  T* orow = out + (size_t)row * dim;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int c0 = (i * 32 + lane) * 4;
+      const float4 gg = *reinterpret_cast<const float4*>(g + c0);
+      const float4 bv = *reinterpret_cast<const float4*>(b + c0);
+      const float o0 = (v[i].x - mean) * rstd * gg.x + bv.x, o1 = (v[i].y - mean) * rstd * gg.y + bv.y;
+      const float o2 = (v[i].z - mean) * rstd * gg.z + bv.z, o3 = (v[i].w - mean) * rstd * gg.w + bv.w;
+      if (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + c0) = make_float4(o0, o1, o2, o3);
+      } else {
+        uint2 u;
+        *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(o0, o1);
+        *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(o2, o3);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(orow) + c0) = u;
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CLS row (:117-120): query 0 of each (b,h) attends all N keys; keys of padded frames are masked
+// (cls_attn_mask :258-260).  Probabilities are the attention map the model returns (:271).
+// grid = B*heads, block = 256, dim_head = 64.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) attn_cls_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ mask,
+                                                       T* __restrict__ out, float* __restrict__ cls_attn, int N, int f,
+                                                       int n, int heads) {
+  extern __shared__ float sm[];
+  float* sc = sm;              // [N]
+  float* q0 = sm + N;          // [64]
+  float* red = q0 + 64;        // [32]
+  float* part = red + 32;      // [4][64]
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int inner = heads * 64, ld = 3 * inner;
+  const T* base = qkv + (size_t)b * N * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 64) q0[tid] = to_f(base[h * 64 + tid]);
+  __syncthreads();
+  float lmax = -FLT_MAX;
+  for (int j = tid; j < N; j += 256) {
+    const T* kr = base + (size_t)j * ld + inner + h * 64;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float kv[8];
+      load8(kr + c * 8, kv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(q0[c * 8 + i], kv[i], s);
+    }
+    if (j > 0 && !mask[b * f + (j - 1) / n]) s = -FLT_MAX;   // masked_fill(~mask, -finfo.max) (:83-84)
+    sc[j] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  float gmax = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) gmax = fmaxf(gmax, red[i]);
+  __syncthreads();
+  float lsum = 0.f;
+  for (int j = tid; j < N; j += 256) {
+    const float e = expf(sc[j] - gmax);
+    sc[j] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  float gsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gsum += red[i];
+  const float inv = 1.0f / gsum;
+  for (int j = tid; j < N; j += 256) {
+    const float pj = sc[j] * inv;
+    sc[j] = pj;
+    if (cls_attn) cls_attn[(size_t)blockIdx.x * N + j] = pj;
+  }
+  __syncthreads();
+  const int d = tid & 63, pr = tid >> 6;
+  float o = 0.f;
+  for (int j = pr; j < N; j += 4) o = fmaf(sc[j], to_f(base[(size_t)j * ld + 2 * inner + h * 64 + d]), o);
+  part[pr * 64 + d] = o;
+  __syncthreads();
+  if (tid < 64) {
+    const float r = (part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]);
+    out[(size_t)b * N * inner + h * 64 + tid] = from_f<T>(r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Patch rows (:122-135).  One block per group:
+//   TIME  group (b,h,patch p): queries = the f frames at patch p, keys = CLS + those f tokens,
+//         key k allowed iff mask[b][k] & identities_mask[b][q][k]  (frame_mask :252-255); CLS always.
+//   SPACE group (b,h,frame fr): queries = the n patches of the frame, keys = CLS + those n tokens, no mask.
+// K/V of the group sit in shared memory as fp32; each warp owns a query at a time.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128) attn_group_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ mask,
+                                                         const uint8_t* __restrict__ idmask, T* __restrict__ out,
+                                                         int f, int n, int heads) {
+  __shared__ float Ks[64][65];
+  __shared__ float Vs[64][65];
+  __shared__ float Qs[4][64];
+  __shared__ float Ps[4][64];
+  const int G = MODE == MT_ATTN_TIME ? n : f;
+  const int Gq = MODE == MT_ATTN_TIME ? f : n;
+  const int Gk = Gq + 1;
+  const int g = blockIdx.x % G;
+  const int h = (blockIdx.x / G) % heads;
+  const int b = blockIdx.x / (G * heads);
+  const int N = 1 + f * n, inner = heads * 64, ld = 3 * inner;
+  const T* base = qkv + (size_t)b * N * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto token = [&](int j) -> int {  // j = 0 is CLS, j >= 1 the (j-1)-th member of the group
+    if (j == 0) return 0;
+    return MODE == MT_ATTN_TIME ? 1 + (j - 1) * n + g : 1 + g * n + (j - 1);
+  };
+  for (int e = tid; e < Gk * 8; e += 128) {
+    const int j = e >> 3, c = e & 7;
+    const T* row = base + (size_t)token(j) * ld + h * 64 + c * 8;
+    float kv[8], vv[8];
+    load8(row + inner, kv);
+    load8(row + 2 * inner, vv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { Ks[j][c * 8 + i] = kv[i]; Vs[j][c * 8 + i] = vv[i]; }
+  }
+  __syncthreads();
+  for (int i = warp; i < Gq; i += 4) {
+    const int tq = token(i + 1);
+    const T* qr = base + (size_t)tq * ld + h * 64;
+    Qs[warp][lane] = to_f(qr[lane]);
+    Qs[warp][lane + 32] = to_f(qr[lane + 32]);
+    __syncwarp();
+    float s[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int j = lane + r * 32;
+      float a = -FLT_MAX;
+      if (j < Gk) {
+        a = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) a = fmaf(Qs[warp][d], Ks[j][d], a);
+        if (MODE == MT_ATTN_TIME && j > 0) {
+          const bool ok = mask[b * f + (j - 1)] && idmask[((size_t)b * f + i) * f + (j - 1)];
+          if (!ok) a = -FLT_MAX;
+        }
+      }
+      s[r] = a;
+    }
+    const float mx = warp_max(fmaxf(s[0], s[1]));
+    const float e0 = (lane < Gk) ? expf(s[0] - mx) : 0.f;
+    const float e1 = (lane + 32 < Gk) ? expf(s[1] - mx) : 0.f;
+    const float inv = 1.0f / warp_sum(e0 + e1);
+    Ps[warp][lane] = e0 * inv;
+    Ps[warp][lane + 32] = e1 * inv;
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < Gk; ++j) {
+      const float pj = Ps[warp][j];
+      o0 = fmaf(pj, Vs[j][lane], o0);
+      o1 = fmaf(pj, Vs[j][lane + 32], o1);
+    }
+    T* orow = out + ((size_t)b * N + tq) * inner + h * 64;
+    orow[lane] = from_f<T>(o0);
+    orow[lane + 32] = from_f<T>(o1);
+    __syncwarp();
+  }
+}
+
+// x[b][0] = cls_token + pos_emb[positions[b][0]] + size_emb[0]   (:231-248)
+__global__ void cls_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos_tab,
+                               const float* __restrict__ size_tab, const long long* __restrict__ positions, float* x,
+                               int tokens, int dim) {
+  const int b = blockIdx.x;
+  const long long p = positions ? positions[(size_t)b * tokens] : 0;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float v = cls[c] + pos_tab[(size_t)p * dim + c];
+    if (size_tab) v += size_tab[c];
+    x[(size_t)b * tokens * dim + c] = v;
+  }
+}
+
+// logits[b] = LayerNorm(x[b][0]) W^T + bias  (:195-198, :270-276); one block (128 threads) per video
+__global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                   const float* __restrict__ be, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, float* __restrict__ logits,
+                                                   int tokens, int dim, int classes) {
+  extern __shared__ float sm[];
+  float* xn = sm;          // [dim]
+  __shared__ float red[4];
+  const float* xr = x + (size_t)blockIdx.x * tokens * dim;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float s = 0.f;
+  for (int c = tid; c < dim; c += 128) s += xr[c];
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  const float mean = ((red[0] + red[1]) + (red[2] + red[3])) / (float)dim;
+  __syncthreads();
+  float q = 0.f;
+  for (int c = tid; c < dim; c += 128) { const float d = xr[c] - mean; q += d * d; }
+  q = warp_sum(q);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  const float rstd = 1.0f / sqrtf(((red[0] + red[1]) + (red[2] + red[3])) / (float)dim + 1e-5f);
+  for (int c = tid; c < dim; c += 128) xn[c] = (xr[c] - mean) * rstd * g[c] + be[c];
+  __syncthreads();
+  for (int k = warp; k < classes; k += 4) {
+    float a = 0.f;
+    for (int c = lane; c < dim; c += 32) a = fmaf(xn[c], w[(size_t)k * dim + c], a);
+    a = warp_sum(a);
+    if (lane == 0) logits[(size_t)blockIdx.x * classes + k] = a + bias[k];
+  }
+}
+
+template <typename T>
+int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, int mode, void* out, float* cls_attn,
+                  int B, int f, int n, int heads, cudaStream_t st) {
+  const int N = 1 + f * n;
+  const T* q = reinterpret_cast<const T*>(qkv);
+  T* o = reinterpret_cast<T*>(out);
+  const size_t smem = (size_t)(N + 64 + 32 + 256) * sizeof(float);
+  {
+    ProfScope prof(st, 4.0 * B * heads * 64.0 * N, (double)B * N * heads * 64 * 2 * sizeof(T), "attn_cls");
+    attn_cls_kernel<T><<<B * heads, 256, smem, st>>>(q, mask, o, cls_attn, N, f, n, heads);
+    MT_LAUNCH_CHECK("attn_cls_kernel");
+  }
+  const double gq = mode == MT_ATTN_TIME ? f : n, groups = (double)B * heads * (mode == MT_ATTN_TIME ? n : f);
+  ProfScope prof(st, 4.0 * groups * 64.0 * gq * (gq + 1), (double)B * N * heads * 64 * 4 * sizeof(T),
+                 mode == MT_ATTN_TIME ? "attn_time" : "attn_space");
+  if (mode == MT_ATTN_TIME)
+    attn_group_kernel<T, MT_ATTN_TIME><<<B * heads * n, 128, 0, st>>>(q, mask, idmask, o, f, n, heads);
+  else
+    attn_group_kernel<T, MT_ATTN_SPACE><<<B * heads * f, 128, 0, st>>>(q, mask, idmask, o, f, n, heads);
+  MT_LAUNCH_CHECK("attn_group_kernel");
+  return MT_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct TsfWs { size_t x, xn, qkv, o, h, total; };
+TsfWs tsf_ws_layout(const mt_tsf_cfg_t& c, int B, int precision) {
+  const size_t es = precision == MT_PREC_FP32 ? 4 : 2;
+  const size_t rows = (size_t)B * (1 + (size_t)c.num_frames * c.num_patches);
+  const size_t inner = (size_t)c.heads * c.dim_head;
+  TsfWs l;
+  size_t off = 0;
+  l.x = off;   off += align_up(rows * c.dim * 4, 1024);
+  l.xn = off;  off += align_up(rows * c.dim * es, 1024);
+  l.qkv = off; off += align_up(rows * 3 * inner * es, 1024);
+  l.o = off;   off += align_up(rows * inner * es, 1024);
+  l.h = off;   off += align_up(rows * 4 * c.dim * es, 1024);
+  l.total = off;
+  return l;
+}
+
+int check_cfg(const mt_tsf_cfg_t* c) {
+  MT_REQUIRE(c, "tsf: null config");
+  MT_REQUIRE(c->dim_head == 64, "tsf: dim_head must be 64 (got %d)", c->dim_head);
+  MT_REQUIRE(c->dim % 128 == 0 && c->dim <= 1024, "tsf: dim must be a multiple of 128 <= 1024 (got %d)", c->dim);
+  MT_REQUIRE(c->depth >= 1 && c->depth <= MT_TSF_MAX_DEPTH, "tsf: depth out of range (%d)", c->depth);
+  MT_REQUIRE(c->num_frames >= 1 && c->num_frames <= 63 && c->num_patches >= 1 && c->num_patches <= 63,
+             "tsf: frames/patches per group must be <= 63 (f=%d n=%d)", c->num_frames, c->num_patches);
+  MT_REQUIRE(c->heads >= 1 && c->channels % 8 == 0 && c->num_classes >= 1, "tsf: bad heads/channels/classes");
+  return MT_OK;
+}
+
+}  // namespace
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" int mt_layernorm_fwd(int precision, const float* x, const float* gamma, const float* beta, void* out,
+                                int rows, int dim, void* stream) {
+  MT_REQUIRE(x && gamma && beta && out && rows > 0, "layernorm: bad argument");
+  MT_REQUIRE(dim % 128 == 0 && dim <= 1024, "layernorm: dim must be a multiple of 128 <= 1024 (got %d)", dim);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (rows + 7) / 8;
+  ProfScope prof(st, 8.0 * rows * dim, (double)rows * dim * (4 + (precision == MT_PREC_FP32 ? 4 : 2)), "layernorm");
+  if (precision == MT_PREC_FP32)
+    layernorm_kernel<float, 8><<<grid, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<float*>(out), rows, dim);
+  else if (precision == MT_PREC_BF16)
+    layernorm_kernel<bf16, 8><<<grid, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<bf16*>(out), rows, dim);
+  else {
+    set_error("layernorm: unknown precision %d", precision);
+    return MT_ERR_ARG;
+  }
+  MT_LAUNCH_CHECK("layernorm_kernel");
+  return MT_OK;
+}
+
+extern "C" int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t* mask, const uint8_t* identities_mask,
+                                   int mode, void* out, float* cls_attn, int batch, int f, int n, int heads,
+                                   int dim_head, void* stream) {
+  MT_REQUIRE(qkv && mask && out, "divided_attn: null pointer");
+  MT_REQUIRE(mode == MT_ATTN_TIME || mode == MT_ATTN_SPACE, "divided_attn: unknown mode %d", mode);
+  MT_REQUIRE(mode == MT_ATTN_SPACE || identities_mask, "divided_attn: time mode needs identities_mask");
+  MT_REQUIRE(dim_head == 64, "divided_attn: dim_head must be 64 (got %d)", dim_head);
+  MT_REQUIRE(batch > 0 && heads > 0 && f >= 1 && f <= 63 && n >= 1 && n <= 63, "divided_attn: bad shape B=%d f=%d n=%d",
+             batch, f, n);
+  MT_REQUIRE((size_t)(1 + f * n + 352) * 4 <= 48 * 1024, "divided_attn: too many tokens (%d)", 1 + f * n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (precision == MT_PREC_FP32)
+    return launch_attn_t<float>(qkv, mask, identities_mask, mode, out, cls_attn, batch, f, n, heads, st);
+  if (precision == MT_PREC_BF16)
+    return launch_attn_t<bf16>(qkv, mask, identities_mask, mode, out, cls_attn, batch, f, n, heads, st);
+  set_error("divided_attn: unknown precision %d", precision);
+  return MT_ERR_ARG;
+}
+
+extern "C" int mt_linear_residual_fwd(int precision, const void* a, const void* w, const float* bias, float* x, int m,
+                                      int n, int k, void* stream) {
+  GemmArgs g{};
+  g.a = a; g.w = w; g.M = m; g.N = n; g.K = k;
+  g.epi.kind = EPI_RESID_F32; g.epi.M = m; g.epi.N = n; g.epi.bias = bias; g.epi.out = x; g.epi.ldo = n;
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mt_linear_geglu_fwd(int precision, const void* a, const void* w, const float* bias, void* out, int m,
+                                   int n, int k, void* stream) {
+  GemmArgs g{};
+  g.a = a; g.w = w; g.M = m; g.N = n; g.K = k;
+  g.epi.kind = EPI_GEGLU; g.epi.M = m; g.epi.N = n; g.epi.bias = bias; g.epi.out = out; g.epi.ldo = n / 2;
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mt_patch_embed_fwd(int precision, const mt_tsf_weights_t* w, const mt_tsf_cfg_t* cfg, const void* feats,
+                                  const int32_t* size_embedding, const int64_t* positions, float* x, int batch,
+                                  void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  MT_REQUIRE(w && feats && x && batch > 0, "patch_embed: bad argument");
+  MT_REQUIRE(!cfg->enable_pos_emb || positions, "patch_embed: positions required when enable-pos-emb is on");
+  MT_REQUIRE(!cfg->enable_size_emb || (size_embedding && w->size_emb), "patch_embed: size embedding inputs missing");
+  const int fn = cfg->num_frames * cfg->num_patches;
+  const long long* pos = cfg->enable_pos_emb ? reinterpret_cast<const long long*>(positions) : nullptr;
+  const float* size_tab = cfg->enable_size_emb ? w->size_emb : nullptr;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cls_row_kernel<<<batch, 128, 0, st>>>(w->cls_token, w->pos_emb, size_tab, pos, x, fn + 1, cfg->dim);
+  MT_LAUNCH_CHECK("cls_row_kernel");
+  GemmArgs g{};
+  g.a = feats; g.w = w->w_patch; g.M = batch * fn; g.N = cfg->dim; g.K = cfg->channels;
+  g.epi.kind = EPI_PATCH_EMBED; g.epi.M = g.M; g.epi.N = g.N; g.epi.bias = w->b_patch; g.epi.out = x;
+  g.epi.ldo = cfg->dim; g.epi.rows_per_batch = fn; g.epi.n_patches = cfg->num_patches; g.epi.frames = cfg->num_frames;
+  g.epi.pos_tab = w->pos_emb; g.epi.size_tab = size_tab; g.epi.positions = pos; g.epi.size_idx = size_embedding;
+  return launch_gemm(precision, g, st);
+}
+
+extern "C" int mt_head_fwd(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* bias,
+                           float* logits, int batch, int tokens, int dim, int num_classes, void* stream) {
+  MT_REQUIRE(x && ln_g && ln_b && w && bias && logits && batch > 0 && tokens > 0 && dim > 0 && num_classes > 0,
+             "head: bad argument");
+  head_kernel<<<batch, 128, (size_t)dim * 4, reinterpret_cast<cudaStream_t>(stream)>>>(x, ln_g, ln_b, w, bias, logits,
+                                                                                       tokens, dim, num_classes);
+  MT_LAUNCH_CHECK("head_kernel");
+  return MT_OK;
+}
+
+extern "C" size_t mt_tsf_workspace_bytes(const mt_tsf_cfg_t* cfg, int batch, int precision) {
+  if (!cfg || batch <= 0) return 0;
+  return tsf_ws_layout(*cfg, batch, precision).total;
+}
+
+extern "C" int mt_tsf_fwd(const mt_tsf_weights_t* w, const mt_tsf_cfg_t* cfg, const void* feats, const uint8_t* mask,
+                          const uint8_t* identities_mask, const int32_t* size_embedding, const int64_t* positions,
+                          float* logits, float* space_attn, float* time_attn, int batch, int precision, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  MT_REQUIRE(w && feats && mask && identities_mask && logits && workspace && batch > 0, "tsf_fwd: bad argument");
+  MT_REQUIRE(precision == MT_PREC_FP32 || precision == MT_PREC_BF16, "tsf_fwd: unknown precision %d", precision);
+  const TsfWs l = tsf_ws_layout(*cfg, batch, precision);
+  if (workspace_bytes < l.total) {
+    set_error("tsf_fwd: workspace too small (%zu < %zu)", workspace_bytes, l.total);
+    return MT_ERR_WORKSPACE;
+  }
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "tsf_fwd: workspace must be 1024-byte aligned");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(ws + l.x);
+  void* xn = ws + l.xn;
+  void* qkv = ws + l.qkv;
+  void* o = ws + l.o;
+  void* hbuf = ws + l.h;
+  const int f = cfg->num_frames, n = cfg->num_patches, D = cfg->dim, H = cfg->heads;
+  const int N = 1 + f * n, rows = batch * N, inner = H * cfg->dim_head;
+
+  rc = mt_patch_embed_fwd(precision, w, cfg, feats, size_embedding, positions, x, batch, stream);
+  if (rc) return rc;
+  for (int l_ = 0; l_ < cfg->depth; ++l_) {
+    const bool last = l_ == cfg->depth - 1;
+    for (int mode = 0; mode < 2; ++mode) {   // time, then space (:264-267)
+      const mt_attn_weights_t& aw = mode == 0 ? w->time_attn[l_] : w->space_attn[l_];
+      float* amap = !last ? nullptr : (mode == 0 ? time_attn : space_attn);
+      rc = mt_layernorm_fwd(precision, x, aw.ln_g, aw.ln_b, xn, rows, D, stream);
+      if (rc) return rc;
+      rc = mt_pointwise_fwd(precision, xn, aw.w_qkv, nullptr, nullptr, 0, nullptr, 0, qkv, rows, 3 * inner, D, stream);
+      if (rc) return rc;
+      rc = mt_divided_attn_fwd(precision, qkv, mask, identities_mask, mode == 0 ? MT_ATTN_TIME : MT_ATTN_SPACE, o, amap,
+                               batch, f, n, H, cfg->dim_head, stream);
+      if (rc) return rc;
+      rc = mt_linear_residual_fwd(precision, o, aw.w_out, aw.b_out, x, rows, D, inner, stream);
+      if (rc) return rc;
+    }
+    const mt_ff_weights_t& fw = w->ff[l_];
+    rc = mt_layernorm_fwd(precision, x, fw.ln_g, fw.ln_b, xn, rows, D, stream);
+    if (rc) return rc;
+    rc = mt_linear_geglu_fwd(precision, xn, fw.w1, fw.b1, hbuf, rows, 8 * D, D, stream);
+    if (rc) return rc;
+    rc = mt_linear_residual_fwd(precision, hbuf, fw.w2, fw.b2, x, rows, D, 4 * D, stream);
+    if (rc) return rc;
+  }
+  return mt_head_fwd(x, w->out_ln_g, w->out_ln_b, w->out_w, w->out_b, logits, batch, N, D, cfg->num_classes, stream);
+}

@@ -1,0 +1,152 @@
+"""Tensor-level wrappers over the building-block entry points of include/mintime_b200.h.
+
+Each function takes CUDA torch tensors (torch only provides memory + the current stream), calls the
+C ABI and returns the output tensor.  Used by the per-kernel parity tests and by callers that want
+to schedule the kernels themselves.  No fallbacks: everything raises without the library / a B200.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _prep(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t
+
+
+def _T(precision: str):
+    return _lib.torch_dtype(precision)
+
+
+def pointwise(a, w, shift=None, gate=None, rows_per_gate=0, residual=None, act=0, precision="bf16"):
+    """out[m,n] = act(sum_k a[m,k]*gate[m//rows_per_gate,k]*w[n,k] + shift[n]) + residual[m,n]"""
+    T = _T(precision)
+    _prep(a, T); _prep(w, T)
+    m, k = a.shape
+    n = w.shape[0]
+    _lib.require_device(a.device)
+    out = torch.empty((m, n), dtype=T, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().mt_pointwise_fwd(_lib.prec_id(precision), a.data_ptr(), w.data_ptr(), _lib.ptr(shift),
+                                          _lib.ptr(gate), rows_per_gate, _lib.ptr(residual), act, out.data_ptr(),
+                                          m, n, k, _lib.stream_ptr())
+    _lib.check(rc, "mt_pointwise_fwd")
+    return out
+
+
+def linear_residual_(x, a, w, bias=None, precision="bf16"):
+    """x[m,n] += a @ w.T + bias   (x float32, in place)"""
+    T = _T(precision)
+    _prep(a, T); _prep(w, T); _prep(x, torch.float32)
+    m, k = a.shape
+    n = w.shape[0]
+    _lib.require_device(a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().mt_linear_residual_fwd(_lib.prec_id(precision), a.data_ptr(), w.data_ptr(), _lib.ptr(bias),
+                                                x.data_ptr(), m, n, k, _lib.stream_ptr())
+    _lib.check(rc, "mt_linear_residual_fwd")
+    return x
+
+
+def linear_geglu(a, w_interleaved, bias_interleaved=None, precision="bf16"):
+    T = _T(precision)
+    _prep(a, T); _prep(w_interleaved, T)
+    m, k = a.shape
+    n = w_interleaved.shape[0]
+    _lib.require_device(a.device)
+    out = torch.empty((m, n // 2), dtype=T, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().mt_linear_geglu_fwd(_lib.prec_id(precision), a.data_ptr(), w_interleaved.data_ptr(),
+                                             _lib.ptr(bias_interleaved), out.data_ptr(), m, n, k, _lib.stream_ptr())
+    _lib.check(rc, "mt_linear_geglu_fwd")
+    return out
+
+
+def layernorm(x, gamma, beta, precision="bf16"):
+    _prep(x, torch.float32)
+    rows, dim = x.shape
+    _lib.require_device(x.device)
+    out = torch.empty((rows, dim), dtype=_T(precision), device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mt_layernorm_fwd(_lib.prec_id(precision), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                          out.data_ptr(), rows, dim, _lib.stream_ptr())
+    _lib.check(rc, "mt_layernorm_fwd")
+    return out
+
+
+def divided_attention(qkv, mask_u8, idmask_u8, mode: str, f: int, n: int, heads: int, dim_head: int = 64,
+                      want_cls_attn: bool = True, precision="bf16"):
+    """qkv (B, 1+f*n, 3*heads*dim_head) with q pre-scaled -> (out (B,N,heads*dim_head), cls_attn (B*heads,N))"""
+    T = _T(precision)
+    _prep(qkv, T)
+    B, N, _ = qkv.shape
+    _lib.require_device(qkv.device)
+    out = torch.empty((B, N, heads * dim_head), dtype=T, device=qkv.device)
+    cls = torch.empty((B * heads, N), dtype=torch.float32, device=qkv.device) if want_cls_attn else None
+    with torch.cuda.device(qkv.device):
+        rc = _lib.load().mt_divided_attn_fwd(_lib.prec_id(precision), qkv.data_ptr(), mask_u8.data_ptr(),
+                                             _lib.ptr(idmask_u8), _lib.ATTN_TIME if mode == "time" else _lib.ATTN_SPACE,
+                                             out.data_ptr(), _lib.ptr(cls), B, f, n, heads, dim_head,
+                                             _lib.stream_ptr())
+    _lib.check(rc, "mt_divided_attn_fwd")
+    return out, cls
+
+
+def stem(x_nhwc, w27x32, shift, precision="bf16"):
+    n, h, w, c = x_nhwc.shape
+    assert c == 3
+    _prep(x_nhwc)
+    _lib.require_device(x_nhwc.device)
+    out = torch.empty((n, (h + 1) // 2, (w + 1) // 2, 32), dtype=_T(precision), device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.load().mt_stem_fwd(_lib.prec_id(precision), x_nhwc.data_ptr(),
+                                     _lib.IN_U8 if x_nhwc.dtype == torch.uint8 else _lib.IN_F32, w27x32.data_ptr(),
+                                     shift.data_ptr(), out.data_ptr(), n, h, w, _lib.stream_ptr())
+    _lib.check(rc, "mt_stem_fwd")
+    return out
+
+
+def dwconv(x_nhwc, w_taps, shift, k: int, s: int, precision="bf16"):
+    """-> (out NHWC, pool_sum (n,c) float32)"""
+    T = _T(precision)
+    _prep(x_nhwc, T)
+    n, h, w, c = x_nhwc.shape
+    _lib.require_device(x_nhwc.device)
+    out = torch.empty((n, (h + s - 1) // s, (w + s - 1) // s, c), dtype=T, device=x_nhwc.device)
+    pool = torch.zeros((n, c), dtype=torch.float32, device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.load().mt_dwconv_fwd(_lib.prec_id(precision), x_nhwc.data_ptr(), w_taps.data_ptr(), shift.data_ptr(),
+                                       out.data_ptr(), pool.data_ptr(), n, h, w, c, k, s, _lib.stream_ptr())
+    _lib.check(rc, "mt_dwconv_fwd")
+    return out, pool
+
+
+def se_gate(pool_sum, hw: int, wr, br, we, be):
+    n, c = pool_sum.shape
+    sq = wr.shape[0]
+    _lib.require_device(pool_sum.device)
+    gate = torch.empty((n, c), dtype=torch.float32, device=pool_sum.device)
+    with torch.cuda.device(pool_sum.device):
+        rc = _lib.load().mt_se_gate_fwd(pool_sum.data_ptr(), hw, wr.data_ptr(), br.data_ptr(), we.data_ptr(),
+                                        be.data_ptr(), gate.data_ptr(), n, c, sq, _lib.stream_ptr())
+    _lib.check(rc, "mt_se_gate_fwd")
+    return gate
+
+
+def head(x, ln_g, ln_b, w, bias):
+    B, tokens, dim = x.shape
+    classes = w.shape[0]
+    _lib.require_device(x.device)
+    logits = torch.empty((B, classes), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mt_head_fwd(x.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                     logits.data_ptr(), B, tokens, dim, classes, _lib.stream_ptr())
+    _lib.check(rc, "mt_head_fwd")
+    return logits

@@ -1,0 +1,180 @@
+"""CPU tests: host-side logic, state_dict compatibility, packing layouts, C-ABI symbol export.
+No GPU compute is invoked here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mintime_b200
+from mintime_b200 import _lib, spec, synth, weights
+from mintime_b200.efficientnet import EfficientNet
+from mintime_b200.size_invariant_timesformer import SizeInvariantTimeSformer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mintime_b200.h")).read()
+    declared = set(re.findall(r"\b(mt_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)            # must exist: built by __graft_entry__.build()
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.mt_abi_version.restype = ctypes.c_int
+    assert lib.mt_abi_version() == 1
+    lib.mt_last_error.restype = ctypes.c_char_p
+    assert lib.mt_last_error() == b""
+
+
+def test_argument_validation_without_gpu():
+    """invalid shapes are rejected on the host before any CUDA call (status < 0 + message)."""
+    lib = _lib.load()
+    rc = lib.mt_layernorm_fwd(1, 8, 8, 8, 8, 4, 100, None)      # dim not a multiple of 128
+    assert rc == -1 and b"multiple of 128" in lib.mt_last_error()
+    rc = lib.mt_pointwise_fwd(1, 8, 8, None, None, 0, None, 0, 8, 4, 12, 16, None)   # N % 8 != 0
+    assert rc == -1 and b"multiples of 8" in lib.mt_last_error()
+    rc = lib.mt_divided_attn_fwd(1, 8, 8, 8, 0, 8, None, 1, 16, 49, 8, 32, None)     # dim_head != 64
+    assert rc == -1 and b"dim_head" in lib.mt_last_error()
+    assert lib.mt_effnet_b0_workspace_bytes(0, 1) == 0
+    assert lib.mt_effnet_b0_workspace_bytes(4, 1) * 2 > lib.mt_effnet_b0_workspace_bytes(4, 0) > \
+        lib.mt_effnet_b0_workspace_bytes(4, 1) > 0
+
+
+def test_effnet_state_dict_matches_reference_names():
+    sd = synth.make_effnet_state_dict(1)
+    m = EfficientNet.from_name("efficientnet-b0")
+    own = m.state_dict()
+    assert len(own) == 360 and set(own) == set(sd)
+    for k in own:
+        assert own[k].shape == sd[k].shape, k
+    m.load_state_dict(sd, strict=True)
+    # names parsed by the reference's partial-unfreeze logic (train.py:159-167)
+    for name, _ in m.named_parameters():
+        if name.startswith("_blocks."):
+            assert 0 <= int(name.split(".")[1]) < 16
+    with pytest.raises(ValueError):
+        EfficientNet.from_name("efficientnet-b9")
+
+
+def test_load_matching_state_dict_semantics():
+    sd = synth.make_effnet_state_dict(2)
+    m = EfficientNet.from_name("efficientnet-b0")
+    renamed = {"efficient_net." + k: v for k, v in sd.items()}
+    renamed["some.unknown.key"] = torch.zeros(3)
+    m.load_matching_state_dict(renamed)               # model.py:368-378
+    assert torch.equal(m.state_dict()["_blocks.3._project_conv.weight"], sd["_blocks.3._project_conv.weight"])
+
+
+def test_tsf_state_dict_matches_reference_names():
+    for f in (8, 16):
+        cfg = spec.default_tsf_config(num_frames=f)
+        sd = synth.make_tsf_state_dict(cfg, 3)
+        m = SizeInvariantTimeSformer(config=cfg, require_attention=True)
+        own = m.state_dict()
+        assert set(own) == set(sd)
+        for k in own:
+            assert own[k].shape == sd[k].shape, k
+        m.load_state_dict(sd, strict=True)
+        assert sum(p.numel() for p in m.parameters()) == (68_894_721 if f == 16 else None) or f == 8
+        assert m.no_weight_decay() == {"pos_emb", "cls_token", "size_emb"}
+
+
+def test_tsf_config_quirks():
+    cfg = spec.default_tsf_config()
+    cfg["model"]["shift-tokens"] = True
+    with pytest.raises(NotImplementedError):
+        SizeInvariantTimeSformer(config=cfg)
+    cfg = spec.default_tsf_config()
+    m = SizeInvariantTimeSformer(config=cfg)
+    with pytest.raises(ValueError):       # f must equal config num-frames (reference :252)
+        m(torch.zeros(1, 8, 1280, 7, 7), mask=torch.ones(1, 8, dtype=torch.bool),
+          identities_mask=torch.ones(1, 8, 8, dtype=torch.bool), size_embedding=torch.zeros(1, 8, dtype=torch.int32),
+          positions=torch.zeros(1, 393, dtype=torch.int64))
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device the product path raises instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = EfficientNet.from_name("efficientnet-b0").eval()
+    with pytest.raises(_lib.MintimeError):
+        m(torch.zeros(1, 3, 224, 224))
+    cfg = spec.default_tsf_config()
+    t = SizeInvariantTimeSformer(config=cfg)
+    with pytest.raises(_lib.MintimeError):
+        t(torch.zeros(1, 16, 1280, 7, 7), mask=torch.ones(1, 16, dtype=torch.bool),
+          identities_mask=torch.ones(1, 16, 16, dtype=torch.bool),
+          size_embedding=torch.zeros(1, 16, dtype=torch.int32), positions=torch.zeros(1, 785, dtype=torch.int64))
+    e = EfficientNet.from_name("efficientnet-b0")      # train mode is not implemented: loud, not silent
+    with pytest.raises(NotImplementedError):
+        e(torch.zeros(1, 3, 224, 224))
+
+
+def test_block_table_in_csrc_matches_spec():
+    src = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "effnet.cu")).read()
+    body = src[src.index("kBlocks[16] = {"):]
+    body = body[:body.index("};")]
+    rows = re.findall(r"\{(\d+), (\d+), (\d+), (\d+), (\d+), (\d+)\}", body)
+    assert len(rows) == 16
+    for r, s in zip(rows, spec.B0_BLOCKS):
+        assert tuple(map(int, r)) == (s.kernel, s.stride, s.expand, s.cin, s.cout, s.hw_in)
+    # TF-SAME low-side padding per block (last column)
+    assert [b.pad_lo for b in spec.B0_BLOCKS] == [1, 0, 1, 1, 2, 0, 1, 1, 2, 2, 2, 1, 2, 2, 2, 1]
+
+
+def test_bn_fold_and_layouts():
+    sd = synth.make_effnet_state_dict(5)
+    pk = weights.pack_effnet(sd, "fp32", "cpu")
+    # tensors are kept in pack order: stem w, stem shift, ...
+    stem_w, stem_shift = pk.keep[0], pk.keep[1]
+    scale = sd["_bn0.weight"] / torch.sqrt(sd["_bn0.running_var"] + spec.BN_EPS)
+    ref = (sd["_conv_stem.weight"] * scale[:, None, None, None]).permute(2, 3, 1, 0).reshape(27, 32)
+    assert torch.allclose(stem_w, ref, atol=1e-7)
+    assert torch.allclose(stem_shift, sd["_bn0.bias"] - sd["_bn0.running_mean"] * scale, atol=1e-6)
+    x = torch.randn(2, 3, 8, 8)
+    y_ref = torch.nn.functional.batch_norm(
+        torch.nn.functional.conv2d(x, sd["_conv_stem.weight"]), sd["_bn0.running_mean"], sd["_bn0.running_var"],
+        sd["_bn0.weight"], sd["_bn0.bias"], False, 0.0, spec.BN_EPS)
+    w = stem_w.reshape(3, 3, 3, 32).permute(3, 2, 0, 1)
+    y = torch.nn.functional.conv2d(x, w) + stem_shift[None, :, None, None]
+    assert torch.allclose(y, y_ref, atol=1e-4, rtol=1e-4)
+
+
+def test_geglu_interleave_roundtrip():
+    t = torch.arange(256 * 3, dtype=torch.float32).reshape(256, 3)
+    p = weights.geglu_interleave(t)
+    h = 128
+    for r in range(256):
+        blk, within = divmod(r, 64)
+        src = blk * 32 + within if within < 32 else h + blk * 32 + (within - 32)
+        assert torch.equal(p[r], t[src])
+
+
+def test_pack_tsf_layout():
+    cfg = spec.default_tsf_config(num_frames=8)
+    sd = synth.make_tsf_state_dict(cfg, 7)
+    sd = {"module." + k: v for k, v in sd.items()}      # DataParallel checkpoint (predict.py:378-388)
+    pk = weights.pack_tsf(sd, cfg, "bf16", "cpu")
+    assert pk.struct.w_patch and pk.struct.size_emb and pk.struct.ff[8].w2 and not pk.struct.ff[9].w2
+    wq = [t for t in pk.keep if t.shape == (1536, 512)][0]
+    ref = sd["module.layers.0.0.fn.to_qkv.weight"].clone()
+    ref[:512] *= 0.125
+    assert torch.equal(wq, ref.to(torch.bfloat16))
+
+
+def test_synthetic_clip_metadata_contract():
+    for ids, f in ((1, 16), (2, 16), (3, 16), (4, 16), (2, 8)):
+        meta = synth.make_batch_meta(3, f, [ids], seed=5)
+        m, im, se, pos = meta["mask"], meta["identities_mask"], meta["size_embedding"], meta["positions"]
+        assert m.shape == (3, f) and im.shape == (3, f, f) and se.shape == (3, f) and pos.shape == (3, 1 + f * 49)
+        assert m.dtype == torch.bool and im.dtype == torch.bool and se.dtype == torch.int32 and pos.dtype == torch.int64
+        assert (pos[:, 0] == 0).all() and pos.max() <= f * 49 and pos[:, 1:].min() >= 1
+        assert sum(synth.identity_slots(f, ids)) == f
+        assert torch.equal(im, im.transpose(1, 2))                      # block diagonal
+        assert ((se == 0) == (~m)).all()                                # padded slots carry size 0
+        assert im.diagonal(dim1=1, dim2=2).all()
+    assert synth.identity_slots(16, 3) == [5, 5, 6] and synth.identity_slots(16, 4) == [5, 5, 2, 4]
