@@ -170,15 +170,25 @@ int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t* mask, con
 int mt_stem_fwd(int precision, const void* x, int x_dtype, const float* w, const float* shift, void* out, int n_img,
                 int h, int w_, void* stream);
 
-/* Depthwise kxk stride s conv with TF-SAME padding + BN + swish, plus the SE squeeze sums
+/* Depthwise kxk stride s conv with TF-SAME padding + BN + swish, plus partial sums for the SE squeeze
  * (model.py:105-107,110): in T NHWC [n_img][h][w][c] -> out T NHWC [n_img][ceil(h/s)][ceil(w/s)][c];
- * pool_sum f32 [n_img][c] must be zeroed by the caller and receives sum over pixels of out. */
-int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_sum,
+ * pool_part f32 [n_img][n_chunks][c], n_chunks = mt_dwconv_chunks(h, w, s): sum of out over each chunk of
+ * output pixels (every entry is written; no zero-init; deterministic -- no atomics). */
+int mt_dwconv_chunks(int h, int w_, int s);
+int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
                   int n_img, int h, int w_, int c, int k, int s, void* stream);
 
-/* SE excitation (model.py:111-115): gate[i][c] = sigmoid(We*swish(Wr*(pool_sum[i]/hw) + br) + be) */
-int mt_se_gate_fwd(const float* pool_sum, int hw, const float* wr, const float* br, const float* we, const float* be,
-                   float* gate, int n_img, int c, int sq, void* stream);
+/* SE excitation (model.py:110-115): mean = sum_chunks(pool_part)/hw;  gate[i][c] = sigmoid(We*swish(Wr*mean + br) + be) */
+int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br, const float* we,
+                   const float* be, float* gate, int n_img, int c, int sq, void* stream);
+
+/* One MBConvBlock.forward in eval mode (model.py:89-128): in T NHWC [n_img][hw_in][hw_in][cin] ->
+ * out T NHWC [n_img][ceil(hw_in/stride)]^2[cout].  mt_effnet_b0_block_spec(i, &spec) fills the B0 table entry i. */
+typedef struct { int kernel, stride, expand, cin, cout, hw_in; } mt_mbconv_spec_t;
+int mt_effnet_b0_block_spec(int index, mt_mbconv_spec_t* spec);
+size_t mt_mbconv_workspace_bytes(const mt_mbconv_spec_t* spec, int n_img, int precision);
+int mt_mbconv_fwd(int precision, const mt_mbconv_spec_t* spec, const mt_mbconv_t* w, const void* in, void* out,
+                  int n_img, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Classification head (:195-198,270-276): logits[b] = LayerNorm(x[b][0]) * W^T + bias */
 int mt_head_fwd(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* bias, float* logits,

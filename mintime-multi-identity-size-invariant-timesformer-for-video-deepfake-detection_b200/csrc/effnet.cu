@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const TIN* __restrict__ x, co
 }
 
 // ---------------------------------------------------------------------------------------------------
-// depthwise kxk stride s + BN + swish, and the per-(image, channel) sums the squeeze-excite needs
-// (model.py:105-107,110).  grid = (pixel chunks, 64-channel chunks, images); a warp walks pixels,
+// depthwise kxk stride s + BN + swish, and per-(image, pixel chunk, channel) partial sums for the
+// squeeze-excite average pool (model.py:105-107,110).  grid = (pixel chunks, 64-channel chunks, images); a warp walks pixels,
 // its lanes hold channel pairs so every tap is one coalesced 128-byte (bf16) row segment.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 load2(const float* p) { return *reinterpret_cast<const float2*>(p); }
@@ -95,7 +95,7 @@ constexpr int kDwPixPerBlock = 256;
 template <typename T, int K, int S>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                      const float* __restrict__ shift, T* __restrict__ out,
-                                                     float* __restrict__ pool_sum, int H, int W, int Ho, int Wo, int C,
+                                                     float* __restrict__ pool_part, int H, int W, int Ho, int Wo, int C,
                                                      int pad_lo) {
   __shared__ float red[8][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, c
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-      atomicAdd(pool_sum + (size_t)img * C + cc, s);
+      // one writer per (image, pixel chunk, channel): deterministic, no zero-init needed
+      pool_part[((size_t)img * gridDim.x + blockIdx.x) * C + cc] = s;
     }
   }
 }
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, c
 // ---------------------------------------------------------------------------------------------------
 // SE excitation (model.py:111-115): gate = sigmoid(We * swish(Wr * mean + br) + be); one block per image
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_sum, float inv_hw,
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int n_chunks, float inv_hw,
                                                       const float* __restrict__ wr, const float* __restrict__ br,
                                                       const float* __restrict__ we, const float* __restrict__ be,
                                                       float* __restrict__ gate, int C, int SQ) {
@@ -166,7 +167,11 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   float* mean = sm;        // [C]
   float* sq = sm + C;      // [SQ]
   const int img = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool_sum[(size_t)img * C + c] * inv_hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double acc = 0.0;
+    for (int j = 0; j < n_chunks; ++j) acc += (double)pool_part[((size_t)img * n_chunks + j) * C + c];
+    mean[c] = (float)(acc * (double)inv_hw);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int j = warp; j < SQ; j += nwarps) {
@@ -222,26 +227,44 @@ int launch_dw_t(const void* in, const float* w, const float* shift, void* out, f
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct EffnetWs {
-  size_t act_a, act_b, exp, dw, pool, gate, total;
-};
+int dw_chunks(int hw_out) { return (hw_out * hw_out + kDwPixPerBlock - 1) / kDwPixPerBlock; }
+
+struct BlockWs { size_t exp, dw, pool, gate, total; };
+BlockWs block_ws_layout(const mt_mbconv_spec_t& b, int n_img, int precision) {
+  const size_t es = precision == MT_PREC_FP32 ? 4 : 2;
+  const size_t ho = (b.hw_in + b.stride - 1) / b.stride, cexp = (size_t)b.cin * b.expand;
+  BlockWs l;
+  size_t off = 0;
+  l.exp = off;  off += b.expand != 1 ? align_up((size_t)b.hw_in * b.hw_in * cexp * n_img * es, 1024) : 0;
+  l.dw = off;   off += align_up(ho * ho * cexp * n_img * es, 1024);
+  l.pool = off; off += align_up((size_t)dw_chunks((int)ho) * cexp * n_img * 4, 1024);
+  l.gate = off; off += align_up(cexp * n_img * 4, 1024);
+  l.total = off;
+  return l;
+}
+
+mt_mbconv_spec_t spec_of(int i) {
+  const BlockSpec& b = kBlocks[i];
+  mt_mbconv_spec_t s;
+  s.kernel = b.k; s.stride = b.s; s.expand = b.e; s.cin = b.cin; s.cout = b.cout; s.hw_in = b.hw;
+  return s;
+}
+
+struct EffnetWs { size_t act_a, act_b, block, total; };
 EffnetWs effnet_ws_layout(int n_img, int precision) {
   const size_t es = precision == MT_PREC_FP32 ? 4 : 2;
-  size_t max_io = (size_t)112 * 112 * 32, max_exp = 0, max_dw = 0;
-  for (const BlockSpec& b : kBlocks) {
-    const size_t ho = (b.hw + b.s - 1) / b.s;
+  size_t max_io = (size_t)112 * 112 * 32, max_block = 0;
+  for (int i = 0; i < 16; ++i) {
+    const mt_mbconv_spec_t b = spec_of(i);
+    const size_t ho = (b.hw_in + b.stride - 1) / b.stride;
     max_io = std::max(max_io, ho * ho * b.cout);
-    if (b.e != 1) max_exp = std::max(max_exp, (size_t)b.hw * b.hw * b.cin * b.e);
-    max_dw = std::max(max_dw, ho * ho * b.cin * b.e);
+    max_block = std::max(max_block, block_ws_layout(b, n_img, precision).total);
   }
   EffnetWs l;
   size_t off = 0;
   l.act_a = off; off += align_up(max_io * n_img * es, 1024);
   l.act_b = off; off += align_up(max_io * n_img * es, 1024);
-  l.exp = off;   off += align_up(max_exp * n_img * es, 1024);
-  l.dw = off;    off += align_up(max_dw * n_img * es, 1024);
-  l.pool = off;  off += align_up((size_t)1152 * n_img * 4, 1024);
-  l.gate = off;  off += align_up((size_t)1152 * n_img * 4, 1024);
+  l.block = off; off += max_block;
   l.total = off;
   return l;
 }
@@ -265,25 +288,32 @@ extern "C" int mt_stem_fwd(int precision, const void* x, int x_dtype, const floa
   return MT_ERR_ARG;
 }
 
+extern "C" int mt_dwconv_chunks(int h, int w_, int s) {
+  if (h <= 0 || w_ <= 0 || s <= 0) return 0;
+  return (((h + s - 1) / s) * ((w_ + s - 1) / s) + kDwPixPerBlock - 1) / kDwPixPerBlock;
+}
+
 extern "C" int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out,
-                             float* pool_sum, int n_img, int h, int w_, int c, int k, int s, void* stream) {
-  MT_REQUIRE(in && w && shift && out && pool_sum, "dwconv: null pointer");
+                             float* pool_part, int n_img, int h, int w_, int c, int k, int s, void* stream) {
+  MT_REQUIRE(in && w && shift && out && pool_part, "dwconv: null pointer");
   MT_REQUIRE(n_img > 0 && h > 0 && w_ > 0 && c > 0 && c % 2 == 0, "dwconv: bad shape n=%d h=%d w=%d c=%d", n_img, h, w_, c);
   MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_sum, n_img, h, w_, c, k, s, st);
-  if (precision == MT_PREC_BF16) return launch_dw_t<bf16>(in, w, shift, out, pool_sum, n_img, h, w_, c, k, s, st);
+  if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, st);
+  if (precision == MT_PREC_BF16) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, st);
   set_error("dwconv: unknown precision %d", precision);
   return MT_ERR_ARG;
 }
 
-extern "C" int mt_se_gate_fwd(const float* pool_sum, int hw, const float* wr, const float* br, const float* we,
-                              const float* be, float* gate, int n_img, int c, int sq, void* stream) {
-  MT_REQUIRE(pool_sum && wr && br && we && be && gate, "se_gate: null pointer");
-  MT_REQUIRE(n_img > 0 && c > 0 && sq > 0 && hw > 0 && (size_t)(c + sq) * 4 <= 48 * 1024, "se_gate: bad shape");
-  ProfScope prof(reinterpret_cast<cudaStream_t>(stream), 4.0 * n_img * (double)c * sq, (double)n_img * c * 8, "se_gate");
+extern "C" int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br,
+                              const float* we, const float* be, float* gate, int n_img, int c, int sq, void* stream) {
+  MT_REQUIRE(pool_part && wr && br && we && be && gate, "se_gate: null pointer");
+  MT_REQUIRE(n_img > 0 && c > 0 && sq > 0 && hw > 0 && n_chunks > 0 && (size_t)(c + sq) * 4 <= 48 * 1024,
+             "se_gate: bad shape");
+  ProfScope prof(reinterpret_cast<cudaStream_t>(stream), 4.0 * n_img * (double)c * sq,
+                 (double)n_img * c * 4 * (n_chunks + 1), "se_gate");
   se_gate_kernel<<<n_img, 256, (size_t)(c + sq) * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
-      pool_sum, 1.0f / (float)hw, wr, br, we, be, gate, c, sq);
+      pool_part, n_chunks, 1.0f / (float)hw, wr, br, we, be, gate, c, sq);
   MT_LAUNCH_CHECK("se_gate_kernel");
   return MT_OK;
 }
@@ -297,6 +327,62 @@ extern "C" int mt_pointwise_fwd(int precision, const void* a, const void* w, con
   g.epi.kind = EPI_STORE; g.epi.M = m; g.epi.N = n;
   g.epi.bias = shift; g.epi.act = act; g.epi.resid = residual; g.epi.out = out; g.epi.ldo = n;
   return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mt_effnet_b0_block_spec(int index, mt_mbconv_spec_t* spec) {
+  MT_REQUIRE(spec && index >= 0 && index < 16, "block_spec: index must be in 0..15");
+  *spec = spec_of(index);
+  return MT_OK;
+}
+
+extern "C" size_t mt_mbconv_workspace_bytes(const mt_mbconv_spec_t* spec, int n_img, int precision) {
+  if (!spec || n_img <= 0) return 0;
+  return block_ws_layout(*spec, n_img, precision).total;
+}
+
+// MBConvBlock.forward, eval mode (model.py:89-128):
+//   [expand 1x1 + BN + swish] -> depthwise + BN + swish (+ SE squeeze partials) -> SE gate ->
+//   project 1x1 (SE gate applied to its input) + BN (+ skip)
+extern "C" int mt_mbconv_fwd(int precision, const mt_mbconv_spec_t* spec, const mt_mbconv_t* w, const void* in,
+                             void* out, int n_img, void* workspace, size_t workspace_bytes, void* stream) {
+  MT_REQUIRE(spec && w && in && out && workspace && n_img > 0, "mbconv: bad argument");
+  MT_REQUIRE(precision == MT_PREC_FP32 || precision == MT_PREC_BF16, "mbconv: unknown precision %d", precision);
+  const mt_mbconv_spec_t& b = *spec;
+  MT_REQUIRE((b.kernel == 3 || b.kernel == 5) && (b.stride == 1 || b.stride == 2) && b.expand >= 1 && b.cin % 8 == 0 &&
+                 b.cout % 8 == 0 && b.hw_in > 0,
+             "mbconv: unsupported block k=%d s=%d e=%d cin=%d cout=%d", b.kernel, b.stride, b.expand, b.cin, b.cout);
+  const BlockWs l = block_ws_layout(b, n_img, precision);
+  if (workspace_bytes < l.total) {
+    set_error("mbconv: workspace too small (%zu < %zu)", workspace_bytes, l.total);
+    return MT_ERR_WORKSPACE;
+  }
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "mbconv: workspace must be 1024-byte aligned");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* bexp = ws + l.exp;
+  void* bdw = ws + l.dw;
+  float* pool = reinterpret_cast<float*>(ws + l.pool);
+  float* gate = reinterpret_cast<float*>(ws + l.gate);
+  const int cexp = b.cin * b.expand;
+  const int ho = (b.hw_in + b.stride - 1) / b.stride;
+  const int sq = std::max(1, b.cin / 4);     // max(1, int(cin * 0.25)), model.py:78
+  const void* dw_in = in;
+  int rc;
+  if (b.expand != 1) {
+    MT_REQUIRE(w->expand.w, "mbconv: expand weights missing");
+    rc = mt_pointwise_fwd(precision, in, w->expand.w, w->expand.shift, nullptr, 0, nullptr, 1, bexp,
+                          n_img * b.hw_in * b.hw_in, cexp, b.cin, stream);
+    if (rc) return rc;
+    dw_in = bexp;
+  }
+  rc = mt_dwconv_fwd(precision, dw_in, w->dw_w, w->dw_shift, bdw, pool, n_img, b.hw_in, b.hw_in, cexp, b.kernel,
+                     b.stride, stream);
+  if (rc) return rc;
+  rc = mt_se_gate_fwd(pool, dw_chunks(ho), ho * ho, w->se_reduce_w, w->se_reduce_b, w->se_expand_w, w->se_expand_b,
+                      gate, n_img, cexp, sq, stream);
+  if (rc) return rc;
+  const bool skip = b.stride == 1 && b.cin == b.cout;   // model.py:123
+  return mt_pointwise_fwd(precision, bdw, w->project.w, w->project.shift, gate, ho * ho, skip ? in : nullptr, 0, out,
+                          n_img * ho * ho, b.cout, cexp, stream);
 }
 
 extern "C" size_t mt_effnet_b0_workspace_bytes(int n_img, int precision) {
@@ -315,41 +401,14 @@ extern "C" int mt_effnet_b0_fwd(const mt_effnet_b0_weights_t* w, const void* x, 
     return MT_ERR_WORKSPACE;
   }
   MT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "effnet_b0_fwd: workspace must be 1024-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   void* cur = ws + l.act_a;
   void* nxt = ws + l.act_b;
-  void* bexp = ws + l.exp;
-  void* bdw = ws + l.dw;
-  float* pool = reinterpret_cast<float*>(ws + l.pool);
-  float* gate = reinterpret_cast<float*>(ws + l.gate);
-
   int rc = mt_stem_fwd(precision, x, x_dtype, w->stem_w, w->stem_shift, cur, n_img, 224, 224, stream);
   if (rc) return rc;
   for (int i = 0; i < 16; ++i) {
-    const BlockSpec& b = kBlocks[i];
-    const mt_mbconv_t& bw = w->blocks[i];
-    const int cexp = b.cin * b.e;
-    const int ho = (b.hw + b.s - 1) / b.s;
-    const int sq = std::max(1, b.cin / 4);
-    const void* dw_in = cur;
-    if (b.e != 1) {
-      MT_REQUIRE(bw.expand.w, "effnet_b0_fwd: block %d has no expand weights", i);
-      rc = mt_pointwise_fwd(precision, cur, bw.expand.w, bw.expand.shift, nullptr, 0, nullptr, 1, bexp,
-                            n_img * b.hw * b.hw, cexp, b.cin, stream);
-      if (rc) return rc;
-      dw_in = bexp;
-    }
-    cudaError_t e = cudaMemsetAsync(pool, 0, (size_t)n_img * cexp * sizeof(float), st);
-    if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(pool)");
-    rc = mt_dwconv_fwd(precision, dw_in, bw.dw_w, bw.dw_shift, bdw, pool, n_img, b.hw, b.hw, cexp, b.k, b.s, stream);
-    if (rc) return rc;
-    rc = mt_se_gate_fwd(pool, ho * ho, bw.se_reduce_w, bw.se_reduce_b, bw.se_expand_w, bw.se_expand_b, gate, n_img,
-                        cexp, sq, stream);
-    if (rc) return rc;
-    const bool skip = b.s == 1 && b.cin == b.cout;
-    rc = mt_pointwise_fwd(precision, bdw, bw.project.w, bw.project.shift, gate, ho * ho, skip ? cur : nullptr, 0, nxt,
-                          n_img * ho * ho, b.cout, cexp, stream);
+    const mt_mbconv_spec_t b = spec_of(i);
+    rc = mt_mbconv_fwd(precision, &b, &w->blocks[i], cur, nxt, n_img, ws + l.block, l.total - l.block, stream);
     if (rc) return rc;
     std::swap(cur, nxt);
   }

@@ -114,30 +114,53 @@ def stem(x_nhwc, w27x32, shift, precision="bf16"):
 
 
 def dwconv(x_nhwc, w_taps, shift, k: int, s: int, precision="bf16"):
-    """-> (out NHWC, pool_sum (n,c) float32)"""
+    """-> (out NHWC, pool_part (n, n_chunks, c) float32: per-chunk sums of out over output pixels)"""
     T = _T(precision)
     _prep(x_nhwc, T)
     n, h, w, c = x_nhwc.shape
     _lib.require_device(x_nhwc.device)
+    lib = _lib.load()
     out = torch.empty((n, (h + s - 1) // s, (w + s - 1) // s, c), dtype=T, device=x_nhwc.device)
-    pool = torch.zeros((n, c), dtype=torch.float32, device=x_nhwc.device)
+    pool = torch.full((n, lib.mt_dwconv_chunks(h, w, s), c), float("nan"), dtype=torch.float32, device=x_nhwc.device)
     with torch.cuda.device(x_nhwc.device):
-        rc = _lib.load().mt_dwconv_fwd(_lib.prec_id(precision), x_nhwc.data_ptr(), w_taps.data_ptr(), shift.data_ptr(),
-                                       out.data_ptr(), pool.data_ptr(), n, h, w, c, k, s, _lib.stream_ptr())
+        rc = lib.mt_dwconv_fwd(_lib.prec_id(precision), x_nhwc.data_ptr(), w_taps.data_ptr(), shift.data_ptr(),
+                               out.data_ptr(), pool.data_ptr(), n, h, w, c, k, s, _lib.stream_ptr())
     _lib.check(rc, "mt_dwconv_fwd")
     return out, pool
 
 
-def se_gate(pool_sum, hw: int, wr, br, we, be):
-    n, c = pool_sum.shape
+def se_gate(pool_part, hw: int, wr, br, we, be):
+    n, chunks, c = pool_part.shape
     sq = wr.shape[0]
-    _lib.require_device(pool_sum.device)
-    gate = torch.empty((n, c), dtype=torch.float32, device=pool_sum.device)
-    with torch.cuda.device(pool_sum.device):
-        rc = _lib.load().mt_se_gate_fwd(pool_sum.data_ptr(), hw, wr.data_ptr(), br.data_ptr(), we.data_ptr(),
+    _lib.require_device(pool_part.device)
+    gate = torch.empty((n, c), dtype=torch.float32, device=pool_part.device)
+    with torch.cuda.device(pool_part.device):
+        rc = _lib.load().mt_se_gate_fwd(pool_part.data_ptr(), chunks, hw, wr.data_ptr(), br.data_ptr(), we.data_ptr(),
                                         be.data_ptr(), gate.data_ptr(), n, c, sq, _lib.stream_ptr())
     _lib.check(rc, "mt_se_gate_fwd")
     return gate
+
+
+def mbconv(x_nhwc, block_index: int, packed_effnet, precision="bf16"):
+    """One B0 MBConv block (eval) on NHWC input, using the block's weights from weights.pack_effnet()."""
+    T = _T(precision)
+    _prep(x_nhwc, T)
+    lib = _lib.load()
+    spec = _lib.MBConvSpec()
+    _lib.check(lib.mt_effnet_b0_block_spec(block_index, spec), "mt_effnet_b0_block_spec")
+    n, h, w, c = x_nhwc.shape
+    if (h, w, c) != (spec.hw_in, spec.hw_in, spec.cin):
+        raise ValueError(f"block {block_index} expects (n,{spec.hw_in},{spec.hw_in},{spec.cin}), got {tuple(x_nhwc.shape)}")
+    _lib.require_device(x_nhwc.device)
+    ho = (spec.hw_in + spec.stride - 1) // spec.stride
+    out = torch.empty((n, ho, ho, spec.cout), dtype=T, device=x_nhwc.device)
+    prec = _lib.prec_id(precision)
+    ws = torch.empty(lib.mt_mbconv_workspace_bytes(spec, n, prec), dtype=torch.uint8, device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        rc = lib.mt_mbconv_fwd(prec, spec, packed_effnet.struct.blocks[block_index], x_nhwc.data_ptr(), out.data_ptr(), n,
+                               ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "mt_mbconv_fwd")
+    return out
 
 
 def head(x, ln_g, ln_b, w, bias):
