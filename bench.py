@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of MINTIME's hot path on B200:  videos/sec for 16-frame 224x224 clips through
+EfficientNet-B0 -> Size-Invariant TimeSformer (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference            # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one forward of the hot path over one batch of synthetic clips (BASELINE.json configs[1]:
+batch=32 16-frame 1-identity clips per GPU, inference).  `value` times the step with inputs resident
+in HBM; `e2e` times the public nn.Module API fed from pinned HOST buffers (H2D of the clip and its
+masks + D2H of the logits inside the timed region).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "videos_per_sec_16f_224px"
+UNIT = "videos/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi polling during the timed region (B200_PROFILING.md 'clocks' recipe)."""
+
+    def __init__(self, index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median over the upper half of the samples = clocks under load (the poller also sees idle gaps)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_videos_per_sec(batch: int, frames: int, identities, steps: int, warmup: int):
+    """The reference's algorithm on the host cores (oracle port, fp32 eager, all threads)."""
+    from mintime_b200 import synth
+    from mintime_b200.spec import default_tsf_config
+    from oracle import mintime_oracle as orc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = default_tsf_config(num_frames=frames)
+    esd = synth.make_effnet_state_dict(1234)
+    tsd = synth.make_tsf_state_dict(cfg, 4321)
+    meta = synth.make_batch_meta(batch, frames, identities, seed=1234)
+    clip = synth.make_frames(batch, frames, seed=1234, mask=meta["mask"])
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.hot_path_forward(esd, tsd, cfg, clip, meta["mask"], meta["identities_mask"], meta["size_embedding"],
+                                 meta["positions"])
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = args.cpu_batch
+    v, sec, cores = cpu_oracle_videos_per_sec(b, args.frames, args.identities, args.steps, args.warmup)
+    sample = f"{b} clips x {args.frames} frames per step (bounded sample of the batch={args.batch} workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cpu=True),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, cpu=False):
+    ids = ",".join(map(str, args.identities))
+    return {
+        "workload": f"BASELINE.json configs[1]: batch={args.batch} {args.frames}-frame {ids}-identity synthetic 224x224 "
+                    f"clips per GPU, inference (EfficientNet-B0 eval -> SizeInvariantTimeSformer, channels=1280)",
+        "batch_per_gpu": args.batch, "frames": args.frames, "identities": ids, "precision": "f32" if cpu else args.precision,
+        "timing": "CUDA events on the launch stream, max over ranks; per-step input (308 MB fp32 clip batch) and "
+                  "activations exceed the 126 MB L2" if not cpu else "wall clock, torch CPU eager, all host threads",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--identities", type=lambda s: [int(x) for x in s.split(",")], default=[1])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attention-maps", action="store_true", help="also return the CLS attention maps (config 5)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import mintime_b200
+    from mintime_b200 import _lib, synth
+    from mintime_b200.spec import default_tsf_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback for the product path); "
+                         "use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, f = args.batch, args.frames
+    cfg = default_tsf_config(num_frames=f)
+    ext = mintime_b200.EfficientNet.from_name("efficientnet-b0", precision=args.precision)
+    ext.load_state_dict(synth.make_effnet_state_dict(1234))
+    ext = ext.to(dev).eval()
+    model = mintime_b200.SizeInvariantTimeSformer(config=cfg, require_attention=args.attention_maps,
+                                                  precision=args.precision)
+    model.load_state_dict(synth.make_tsf_state_dict(cfg, 4321))
+    model = model.to(dev).eval()
+
+    # every rank processes its own shard of clips (weak scaling: B clips per GPU, no data-path collective)
+    meta = synth.make_batch_meta(B, f, args.identities, seed=1234 + rank)
+    clip_u8 = synth.make_frames(B, f, seed=1234 + rank, mask=meta["mask"], dtype=torch.uint8)
+    clip_dev = clip_u8.to(dev).float()                                   # resident fp32 NHWC, 0..255 (train.py:334)
+    meta_dev = {k: v.to(dev) for k, v in meta.items()}
+    host = {"clip": clip_u8.pin_memory(), **{k: v.pin_memory() for k, v in meta.items()}}
+    logits_host = torch.empty((B, 1), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        with torch.no_grad():
+            x = clip_dev.view(B * f, 224, 224, 3).permute(0, 3, 1, 2)    # train.py:341
+            feats = ext(x)
+            feats = feats.reshape(B, f, 1280, 7, 7)                      # train.py:354
+            return model(feats, mask=meta_dev["mask"], size_embedding=meta_dev["size_embedding"],
+                         identities_mask=meta_dev["identities_mask"], positions=meta_dev["positions"])
+
+    def step_e2e():
+        with torch.no_grad():
+            clip = host["clip"].to(dev, non_blocking=True)               # uint8 NHWC clip, pinned -> HBM
+            m = {k: host[k].to(dev, non_blocking=True) for k in ("mask", "identities_mask", "size_embedding", "positions")}
+            x = clip.view(B * f, 224, 224, 3).permute(0, 3, 1, 2)
+            feats = ext(x).reshape(B, f, 1280, 7, 7)
+            out = model(feats, mask=m["mask"], size_embedding=m["size_embedding"], identities_mask=m["identities_mask"],
+                        positions=m["positions"])
+            logits = out[0] if isinstance(out, tuple) else out
+            logits_host.copy_(logits, non_blocking=True)                 # D2H of the step's result
+            torch.cuda.current_stream().synchronize()                    # the caller reads the logits
+        return logits_host
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    lib = _lib.load()
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.mt_prof_launch_count()
+    ms = timed(step_resident, args.steps, 0)
+    launches = lib.mt_prof_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    # per-kernel CUDA-event times over 2 more steps of the same workload (mt_prof_* hooks in the library)
+    lib.mt_prof_reset()
+    lib.mt_prof_enable(1)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step_resident()
+    torch.cuda.synchronize()
+    lib.mt_prof_enable(0)
+    prof = _lib.profile_collect()
+    lib.mt_prof_reset()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_oracle_videos_per_sec(args.cpu_batch, f, args.identities, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_batch} clips x {f} frames per step, 3 timed steps after 1 warm-up "
+                         f"(oracle = fp32 torch-CPU restatement of the reference), {sec:.2f} s/step"}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peaks = load_peaks()
+    ridge = peaks["tensor"] * 1e12 / (peaks["hbm"] * 1e9)
+    total_ms = sum(p[1] for p in prof) or 1.0
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            traffic = json.load(fh)
+    except Exception:
+        pass
+    kernels = []
+    for name, ms_t, fl, by, cnt in prof:
+        sec = ms_t * 1e-3
+        bound = "tensor" if (by > 0 and fl / by >= ridge and name.startswith("gemm")) else "hbm"
+        ach = fl / sec / 1e12 if bound == "tensor" else by / sec / 1e9
+        peak = peaks["tensor"] if bound == "tensor" else peaks["hbm"]
+        kernels.append({"name": name, "share": ms_t / total_ms, "ms_per_launch": ms_t / cnt, "launches_per_step": cnt / prof_steps,
+                        "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                        "frac": ach / peak, "tflops": fl / sec / 1e12, "gbs": by / sec / 1e9})
+    dom = kernels[0] if kernels else None
+    roofline = None
+    if dom:
+        t = traffic.get(dom["name"])
+        roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": t, "kernel": dom["name"], "share_of_step": dom["share"],
+                    "peak_source": f"{peaks['source']} ({'sustained bf16 cuBLAS' if dom['bound'] == 'tensor' else 'copy'} "
+                                   f"figure of MEASURED_PEAKS.json)",
+                    "ms_per_launch": dom["ms_per_launch"]}
+    n = world
+    h2d = int(host["clip"].numel() * host["clip"].element_size() +
+              sum(host[k].numel() * host[k].element_size() for k in ("mask", "identities_mask", "size_embedding", "positions")))
+    out = {
+        "metric": METRIC, "value": n * B / (ms * 1e-3), "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": n * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": int(logits_host.numel() * 4), "ms_per_step": ms_e2e,
+                "input": "uint8 NHWC clips + masks/positions from pinned host memory"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "kernels": kernels,
+        "sum_kernel_ms_per_step": total_ms / prof_steps,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -43,7 +43,7 @@ int mt_device_check(void);
  *   pointwise conv / linear  : w  T [Cout][Cin]   (BN scale folded into rows), shift f32 [Cout]
  *   depthwise conv           : w  f32 [k*k][C]    (BN scale folded),            shift f32 [C]
  *   stem conv                : w  f32 [27][32]    ((ky*3+kx)*3+ci major, BN scale folded), shift f32 [32]
- *   squeeze-excite           : f32, reduce [Sq][C] + bias [Sq], expand [C][Sq] + bias [C]
+ *   squeeze-excite           : f32, reduce [Sq][C] + bias [Sq], expand TRANSPOSED [Sq][C] + bias [C]
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* w;      /* T   [cout][cin] */
@@ -56,7 +56,7 @@ typedef struct {
   const float* dw_shift;   /* [cexp] */
   const float* se_reduce_w; /* [sq][cexp]                                   model.py:76-80   */
   const float* se_reduce_b; /* [sq] */
-  const float* se_expand_w; /* [cexp][sq] */
+  const float* se_expand_w; /* [sq][cexp] (transposed _se_expand.weight) */
   const float* se_expand_b; /* [cexp] */
   mt_pw_t project;         /* [cout][cexp]                                  model.py:83-86   */
 } mt_mbconv_t;
@@ -172,14 +172,20 @@ int mt_stem_fwd(int precision, const void* x, int x_dtype, const float* w, const
 
 /* Depthwise kxk stride s conv with TF-SAME padding + BN + swish, plus partial sums for the SE squeeze
  * (model.py:105-107,110): in T NHWC [n_img][h][w][c] -> out T NHWC [n_img][ceil(h/s)][ceil(w/s)][c];
- * pool_part f32 [n_img][n_chunks][c], n_chunks = mt_dwconv_chunks(h, w, s): sum of out over each chunk of
- * output pixels (every entry is written; no zero-init; deterministic -- no atomics). */
-int mt_dwconv_chunks(int h, int w_, int s);
+ * pool_part f32 [n_img][n_chunks][c], n_chunks = mt_dwconv_chunks(h, w, c, k, s): sum of out over each chunk
+ * of output pixels (every entry is written; no zero-init; deterministic -- no atomics). */
+int mt_dwconv_chunks(int h, int w_, int c, int k, int s);
 int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
                   int n_img, int h, int w_, int c, int k, int s, void* stream);
 
+/* mt_dwconv_fwd + the SE excitation fused in one launch: the last block to finish an image reduces its pool
+ * partials and computes gate[i][c] (see mt_se_gate_fwd).  counters: i32 [n_img], zero on entry (left zero). */
+int mt_dwconv_se_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
+                     int* counters, const float* wr, const float* br, const float* we_t, const float* be, float* gate,
+                     int n_img, int h, int w_, int c, int k, int s, int sq, void* stream);
+
 /* SE excitation (model.py:110-115): mean = sum_chunks(pool_part)/hw;  gate[i][c] = sigmoid(We*swish(Wr*mean + br) + be) */
-int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br, const float* we,
+int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br, const float* we_t,
                    const float* be, float* gate, int n_img, int c, int sq, void* stream);
 
 /* One MBConvBlock.forward in eval mode (model.py:89-128): in T NHWC [n_img][hw_in][hw_in][cin] ->

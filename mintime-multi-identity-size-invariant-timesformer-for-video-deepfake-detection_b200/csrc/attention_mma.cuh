@@ -1,0 +1,243 @@
+// Tensor-core attention core for the bf16 path (reference size_invariant_timesformer.py:122-135).
+//
+// The divided attention groups are tiny -- time: f queries x (f+1) keys, space: n x (n+1), head dim 64 --
+// 3 % of an attention block's FLOPs, far below one 128-row tcgen05 tile, so the core runs on warp-level
+// mma.sync m16n8k16 (bf16 in, fp32 accumulate) with the softmax held in registers between the two
+// products (QK^T accumulator fragments are re-used as the A operand of PV).  The kernels are bound by
+// streaming qkv from HBM/L2 (cp.async into swizzled shared memory), not by math.
+#pragma once
+#include <float.h>
+
+#include "common.cuh"
+
+namespace mt {
+namespace attn {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// tile of 64-wide bf16 rows (128 B per row), 16-byte chunks XOR-swizzled by (row & 7)
+__device__ __forceinline__ uint8_t* tile_ptr(uint8_t* base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+
+// One 16-query m-tile against NKT*16 (padded) keys held in shared memory.
+//   allow(q_local, key) -> bool decides the mask; keys >= n_keys must be rejected by the caller's allow().
+// Writes the normalised output rows (bf16) back over the Q tile rows (own rows only), 16 x 64.
+template <int NKT, typename Allow>
+__device__ __forceinline__ void attend_mtile(uint8_t* qs, uint8_t* ks, uint8_t* vs, int q_row0, int lane, Allow allow) {
+  constexpr int NT = NKT * 2;                    // 8-key n-tiles of S
+  float s[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+  // ---- S = Q K^T
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {              // 16 head dims per step
+    uint32_t a[4];
+    ldmatrix_x4(a, smem_u32(tile_ptr(qs, q_row0 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4))));
+#pragma unroll
+    for (int jp = 0; jp < NKT; ++jp) {          // 16 keys per ldmatrix.x4
+      uint32_t b[4];
+      ldmatrix_x4(b, smem_u32(tile_ptr(ks, jp * 16 + (lane & 7) + (lane >> 4) * 8, kk * 2 + ((lane >> 3) & 1))));
+      mma_bf16(s[jp * 2], a, b[0], b[1]);
+      mma_bf16(s[jp * 2 + 1], a, b[2], b[3]);
+    }
+  }
+  // ---- masked softmax over keys, rows g (c0,c1) and g+8 (c2,c3)
+  const int g = lane >> 2, t = lane & 3;
+  float mx0 = -FLT_MAX, mx1 = -FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = j * 8 + t * 2 + e;
+      if (!allow(g, key)) s[j][e] = -FLT_MAX;
+      if (!allow(g + 8, key)) s[j][2 + e] = -FLT_MAX;
+      mx0 = fmaxf(mx0, s[j][e]);
+      mx1 = fmaxf(mx1, s[j][2 + e]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      // masked entries hold -FLT_MAX: exp underflows to exactly 0 (the CLS key keeps every row's max finite)
+      s[j][e] = __expf(s[j][e] - mx0);
+      s[j][2 + e] = __expf(s[j][2 + e] - mx1);
+      sum0 += s[j][e];
+      sum1 += s[j][2 + e];
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  // ---- O = P V
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NKT; ++kk) {            // 16 keys per step
+    uint32_t a[4];
+    a[0] = pack2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+    a[1] = pack2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+    a[2] = pack2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+    a[3] = pack2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {            // 16 head dims per ldmatrix.x4.trans
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, smem_u32(tile_ptr(vs, kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4))));
+      mma_bf16(o[dp * 2], a, b[0], b[1]);
+      mma_bf16(o[dp * 2 + 1], a, b[2], b[3]);
+    }
+  }
+  // ---- stage O (bf16) over this m-tile's own Q rows so the caller can write full 128-byte rows
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(tile_ptr(qs, q_row0 + g, j) + t * 4) = pack2(o[j][0], o[j][1]);
+    *reinterpret_cast<uint32_t*>(tile_ptr(qs, q_row0 + g + 8, j) + t * 4) = pack2(o[j][2], o[j][3]);
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SPACE: one block (4 warps) per group (b, h, frame): 49 queries x (CLS + 49) keys, no mask (:266).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_space_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int f,
+                                                             int n, int heads) {
+  __shared__ __align__(1024) uint8_t sm[3 * 64 * 128];
+  uint8_t* qs = sm;
+  uint8_t* ks = sm + 64 * 128;
+  uint8_t* vs = sm + 2 * 64 * 128;
+  const int fr = blockIdx.x % f;
+  const int h = (blockIdx.x / f) % heads;
+  const int b = blockIdx.x / (f * heads);
+  const int N = 1 + f * n, inner = heads * 64, ld = 3 * inner;
+  const bf16* base = qkv + (size_t)b * N * ld + h * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tok0 = 1 + fr * n;                   // first patch token of the frame
+  for (int e = tid; e < 64 * 8; e += 128) {
+    const int r = e >> 3, c = e & 7;
+    // queries: row r = patch r; keys/values: row 0 = CLS, row r = patch r-1
+    if (r < n) cp_async16(tile_ptr(qs, r, c), base + (size_t)(tok0 + r) * ld + c * 8);
+    else *reinterpret_cast<uint4*>(tile_ptr(qs, r, c)) = make_uint4(0, 0, 0, 0);
+    if (r <= n) {
+      const bf16* kr = base + (size_t)(r == 0 ? 0 : tok0 + r - 1) * ld + c * 8;
+      cp_async16(tile_ptr(ks, r, c), kr + inner);
+      cp_async16(tile_ptr(vs, r, c), kr + 2 * inner);
+    } else {
+      *reinterpret_cast<uint4*>(tile_ptr(ks, r, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(tile_ptr(vs, r, c)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int nk = n + 1;
+  if (warp * 16 < n) {
+    attend_mtile<4>(qs, ks, vs, warp * 16, lane, [&](int, int key) { return key < nk; });
+    // rows warp*16 .. +15 of qs now hold O; 8 lanes write one 128-byte row
+    for (int e = lane; e < 16 * 8; e += 32) {
+      const int r = warp * 16 + (e >> 3), c = e & 7;
+      if (r < n)
+        *reinterpret_cast<uint4*>(out + ((size_t)b * N + tok0 + r) * inner + h * 64 + c * 8) =
+            *reinterpret_cast<const uint4*>(tile_ptr(qs, r, c));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TIME: one warp per group (b, h, patch): f queries x (CLS + f) keys with the identity mask (:252-255):
+// key k allowed iff mask[b][k] & identities_mask[b][q][k]; the CLS key always.  4 groups per block.
+// NKT = ceil((f + 1) / 16) key tiles, MT = ceil(f / 16) query tiles.
+// ---------------------------------------------------------------------------------------------------
+template <int NKT, int MT>
+__global__ void __launch_bounds__(128) attn_time_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mask,
+                                                            const uint8_t* __restrict__ idmask, bf16* __restrict__ out,
+                                                            int f, int n, int heads) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  constexpr int kQBytes = MT * 16 * 128, kKBytes = NKT * 16 * 128;
+  constexpr int kWarpBytes = kQBytes + 2 * kKBytes;
+  __shared__ unsigned long long allow_bits[64];  // per query frame: bit k set <=> key k (0 = CLS) allowed
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // blocks are laid out per (b, h): ceil(n / 4) blocks each, one warp per patch position
+  const int blocks_per_bh = (n + 3) / 4;
+  const int bh = blockIdx.x / blocks_per_bh;
+  const int p = (blockIdx.x % blocks_per_bh) * 4 + warp;
+  const int b = bh / heads, h = bh % heads;
+  if (tid < 64) {
+    unsigned long long bits = 1ull;              // CLS key
+    if (tid < f)
+      for (int k = 0; k < f; ++k)
+        if (mask[b * f + k] && idmask[((size_t)b * f + tid) * f + k]) bits |= 1ull << (k + 1);
+    allow_bits[tid] = bits;
+  }
+  uint8_t* qs = dsm + warp * kWarpBytes;
+  uint8_t* ks = qs + kQBytes;
+  uint8_t* vs = ks + kKBytes;
+  const int N = 1 + f * n, inner = heads * 64, ld = 3 * inner;
+  const bf16* base = qkv + (size_t)b * N * ld + h * 64;
+  const bool active = p < n;
+  if (active) {
+    for (int e = lane; e < MT * 16 * 8; e += 32) {
+      const int r = e >> 3, c = e & 7;
+      if (r < f) cp_async16(tile_ptr(qs, r, c), base + (size_t)(1 + r * n + p) * ld + c * 8);
+      else *reinterpret_cast<uint4*>(tile_ptr(qs, r, c)) = make_uint4(0, 0, 0, 0);
+    }
+    for (int e = lane; e < NKT * 16 * 8; e += 32) {
+      const int r = e >> 3, c = e & 7;
+      if (r <= f) {
+        const bf16* kr = base + (size_t)(r == 0 ? 0 : 1 + (r - 1) * n + p) * ld + c * 8;
+        cp_async16(tile_ptr(ks, r, c), kr + inner);
+        cp_async16(tile_ptr(vs, r, c), kr + 2 * inner);
+      } else {
+        *reinterpret_cast<uint4*>(tile_ptr(ks, r, c)) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(tile_ptr(vs, r, c)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();                               // allow_bits + (per-warp) tiles visible
+  if (!active) return;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    attend_mtile<NKT>(qs, ks, vs, mt * 16, lane, [&](int ql, int key) {
+      const int q = mt * 16 + ql;
+      return q < f ? ((allow_bits[q] >> key) & 1ull) != 0 : key == 0;
+    });
+  }
+  for (int e = lane; e < MT * 16 * 8; e += 32) {
+    const int r = e >> 3, c = e & 7;
+    if (r < f)
+      *reinterpret_cast<uint4*>(out + ((size_t)b * N + 1 + r * n + p) * inner + h * 64 + c * 8) =
+          *reinterpret_cast<const uint4*>(tile_ptr(qs, r, c));
+  }
+}
+
+}  // namespace attn
+}  // namespace mt

@@ -28,29 +28,27 @@ __host__ __device__ inline int same_pad_lo(int in, int k, int s) {
 
 // ---------------------------------------------------------------------------------------------------
 // stem: pad(0,1,0,1) + conv3x3 s2 (3 -> 32) + BN + swish   (utils.py:273-276, model.py:276)
-// one thread = one output pixel x 8 output channels
+// one thread = one output pixel x all 32 output channels; filters are broadcast from shared memory
+// (one LDS.128 feeds 4 FMAs), the 64-byte (bf16) output row of a pixel is written by its own thread so a
+// warp writes 2 KiB contiguous.
 // ---------------------------------------------------------------------------------------------------
 template <typename T, typename TIN>
-__global__ void __launch_bounds__(256) stem_kernel(const TIN* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) stem_kernel(const TIN* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ shift, T* __restrict__ out, int n_img,
                                                    int H, int W, int Ho, int Wo, int pad_lo) {
-  __shared__ float ws[27 * 32];
-  __shared__ float sh[32];
+  __shared__ __align__(16) float ws[27 * 32];
+  __shared__ __align__(16) float sh[32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < 32) sh[threadIdx.x] = shift[threadIdx.x];
   __syncthreads();
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n_img * Ho * Wo * 4;
-  if (idx >= total) return;
-  const int oct = (int)(idx & 3);
-  long long pix = idx >> 2;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)n_img * Ho * Wo) return;
   const int ox = (int)(pix % Wo);
-  pix /= Wo;
-  const int oy = (int)(pix % Ho);
-  const int img = (int)(pix / Ho);
-  float acc[8];
+  const int oy = (int)((pix / Wo) % Ho);
+  const int img = (int)(pix / ((long long)Wo * Ho));
+  float acc[32];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const TIN* xi = x + (size_t)img * H * W * 3;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
@@ -64,128 +62,278 @@ __global__ void __launch_bounds__(256) stem_kernel(const TIN* __restrict__ x, co
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float v = (float)px[ci];
-        const float* wr = ws + ((ky * 3 + kx) * 3 + ci) * 32 + oct * 8;
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 32);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i], acc[i]);
-      }
-    }
-  }
-  constexpr bool kExact = sizeof(T) == 4;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = silu<kExact>(acc[i] + sh[oct * 8 + i]);
-  store8(out + ((size_t)(img * Ho + oy) * Wo + ox) * 32 + oct * 8, acc);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// depthwise kxk stride s + BN + swish, and per-(image, pixel chunk, channel) partial sums for the
-// squeeze-excite average pool (model.py:105-107,110).  grid = (pixel chunks, 64-channel chunks, images); a warp walks pixels,
-// its lanes hold channel pairs so every tap is one coalesced 128-byte (bf16) row segment.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 load2(const float* p) { return *reinterpret_cast<const float2*>(p); }
-__device__ __forceinline__ float2 load2(const bf16* p) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-}
-__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
-__device__ __forceinline__ void store2(bf16* p, float a, float b) {
-  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
-}
-
-constexpr int kDwPixPerBlock = 256;
-
-template <typename T, int K, int S>
-__global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
-                                                     const float* __restrict__ shift, T* __restrict__ out,
-                                                     float* __restrict__ pool_part, int H, int W, int Ho, int Wo, int C,
-                                                     int pad_lo) {
-  __shared__ float red[8][64];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int img = blockIdx.z;
-  const int c = blockIdx.y * 64 + lane * 2;
-  const bool active = c < C;
-  float wk[K * K][2];
-  float sh0 = 0.f, sh1 = 0.f;
-  if (active) {
-#pragma unroll
-    for (int t = 0; t < K * K; ++t) {
-      const float2 ww = load2(w + (size_t)t * C + c);
-      wk[t][0] = ww.x; wk[t][1] = ww.y;
-    }
-    sh0 = shift[c]; sh1 = shift[c + 1];
-  }
-  const T* in_img = in + (size_t)img * H * W * C;
-  T* out_img = out + (size_t)img * Ho * Wo * C;
-  const int p_begin = blockIdx.x * kDwPixPerBlock;
-  const int p_end = min(p_begin + kDwPixPerBlock, Ho * Wo);
-  float ps0 = 0.f, ps1 = 0.f;
-  constexpr bool kExact = sizeof(T) == 4;
-  if (active) {
-    for (int p = p_begin + warp; p < p_end; p += 8) {
-      const int oy = p / Wo, ox = p - oy * Wo;
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int iy = oy * S + ky - pad_lo;
-        if (iy < 0 || iy >= H) continue;
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int ix = ox * S + kx - pad_lo;
-          if (ix < 0 || ix >= W) continue;
-          const float2 v = load2(in_img + ((size_t)iy * W + ix) * C + c);
-          a0 = fmaf(v.x, wk[ky * K + kx][0], a0);
-          a1 = fmaf(v.y, wk[ky * K + kx][1], a1);
+        for (int q = 0; q < 8; ++q) {
+          const float4 ww = wr[q];
+          acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
         }
       }
-      a0 = silu<kExact>(a0 + sh0);
-      a1 = silu<kExact>(a1 + sh1);
-      store2(out_img + (size_t)p * C + c, a0, a1);
-      ps0 += a0; ps1 += a1;
     }
   }
-  red[warp][lane * 2] = ps0;
-  red[warp][lane * 2 + 1] = ps1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    const int cc = blockIdx.y * 64 + threadIdx.x;
-    if (cc < C) {
-      float s = 0.f;
+  constexpr bool kExact = sizeof(T) == 4;
+  T* orow = out + (size_t)pix * 32;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-      // one writer per (image, pixel chunk, channel): deterministic, no zero-init needed
-      pool_part[((size_t)img * gridDim.x + blockIdx.x) * C + cc] = s;
-    }
+  for (int o = 0; o < 4; ++o) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = silu<kExact>(acc[o * 8 + i] + sh[o * 8 + i]);
+    store8(orow + o * 8, v);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// SE excitation (model.py:111-115): gate = sigmoid(We * swish(Wr * mean + br) + be); one block per image
+// depthwise kxk stride s + BN + swish, and per-(image, chunk, channel) partial sums for the
+// squeeze-excite average pool (model.py:105-107,110).
+//
+// A thread owns 8 channels (one 16-byte NHWC vector) of an R x SX patch of output pixels and walks the
+// (R-1)*S+K input rows it needs once, holding one input row segment in registers: every input vector
+// is loaded once per thread and feeds up to K*R taps.  Lanes run over channel octets first, so a warp
+// reads whole contiguous pixel rows (C*2 bytes each).  Filters come from L1 (16 B per tap per thread).
+// blockDim = n_oct * SPB (SPB patches side by side), a block makes kDwPasses passes; pool partials are
+// reduced per block in a fixed order (deterministic, no atomics).
 // ---------------------------------------------------------------------------------------------------
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) { load8(p, v); }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  __device__ __forceinline__ float get(int i) const { return v[i]; }
+};
+template <> struct Raw8<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { u = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ float get(int i) const {
+    const uint32_t w = i < 2 ? u.x : (i < 4 ? u.y : (i < 6 ? u.z : u.w));
+    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+  }
+};
+
+constexpr int kDwPasses = 4;
+__host__ __device__ constexpr int dw_sx(int s) { return s == 1 ? 4 : 2; }   // output columns per thread
+// output rows per thread: 2 for 3x3 (4 input rows feed 2 output rows); 1 for 5x5, whose 2-row variant
+// needs 168 registers + spills and leaves 9 warps per SM -- too few to hide the load latency
+__host__ __device__ constexpr int dw_rows(int k) { return k == 3 ? 2 : 1; }
+
+struct DwGeom {
+  int n_oct, spb, threads, patches_x, patches, per_block, chunks;
+};
+inline DwGeom dw_geom(int H, int W, int C, int k, int s) {
+  DwGeom g;
+  const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
+  g.n_oct = C / 8;
+  g.spb = std::max(1, (256 + g.n_oct / 2) / g.n_oct);
+  if (g.n_oct * g.spb > 320) g.spb = std::max(1, 320 / g.n_oct);
+  g.threads = g.n_oct * g.spb;
+  g.patches_x = (Wo + dw_sx(s) - 1) / dw_sx(s);
+  g.patches = g.patches_x * ((Ho + dw_rows(k) - 1) / dw_rows(k));
+  g.per_block = g.spb * kDwPasses;
+  g.chunks = (g.patches + g.per_block - 1) / g.per_block;
+  return g;
+}
+
+// Squeeze-excite tail fused into the depthwise kernel: the LAST block to finish an image (per-image
+// arrival counter) reduces that image's pool partials and runs the two tiny FC layers, so the SE gate
+// costs no extra launch and overlaps with the depthwise work of the other images.
+struct SeArgs {
+  const float* wr;    // [SQ][C]   (null: no fused SE)
+  const float* br;    // [SQ]
+  const float* we_t;  // [SQ][C]
+  const float* be;    // [C]
+  float* gate;        // [n_img][C]
+  int* counters;      // [n_img], zero on entry, zero again on exit
+  int sq;
+  float inv_hw;
+};
+
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                      const float* __restrict__ shift, T* __restrict__ out,
+                                                      float* __restrict__ pool_part, int H, int W, int Ho, int Wo, int C,
+                                                      int pad_lo, int n_oct, int spb, int patches_x, int patches,
+                                                      SeArgs se) {
+  constexpr int SX = dw_sx(S), R = dw_rows(K);
+  constexpr int NIN = (SX - 1) * S + K;          // input columns feeding SX outputs
+  constexpr int NROW = (R - 1) * S + K;          // input rows feeding R output rows
+  extern __shared__ float part[];                // [blockDim][8]
+  const int tid = threadIdx.x;
+  const int oct = tid % n_oct, slot = tid / n_oct;
+  const int c0 = oct * 8;
+  const int img = blockIdx.y;
+  const T* in_img = in + (size_t)img * H * W * C + c0;
+  T* out_img = out + (size_t)img * Ho * Wo * C + c0;
+  float sh[8];
+  load8(shift + c0, sh);
+  float psum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) psum[i] = 0.f;
+  constexpr bool kExact = sizeof(T) == 4;
+
+  for (int pass = 0; pass < kDwPasses; ++pass) {
+    const int pid = (blockIdx.x * kDwPasses + pass) * spb + slot;
+    if (pid >= patches) break;
+    const int oy0 = (pid / patches_x) * R, ox0 = (pid % patches_x) * SX;
+    const int iy0 = oy0 * S - pad_lo, ix0 = ox0 * S - pad_lo;
+    float acc[R][SX][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < SX; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[r][j][i] = 0.f;
+
+#pragma unroll
+    for (int ir = 0; ir < NROW; ++ir) {
+      const int iy = iy0 + ir;
+      if (iy < 0 || iy >= H) continue;          // zero padding rows contribute nothing
+      Raw8<T> row[NIN];
+      const T* rp = in_img + (size_t)iy * W * C;
+#pragma unroll
+      for (int jj = 0; jj < NIN; ++jj) {
+        const int ix = ix0 + jj;
+        if (ix >= 0 && ix < W) row[jj].load(rp + (size_t)ix * C);
+        else row[jj].zero();
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int ky = ir - r * S;               // compile-time after unrolling
+        if (ky < 0 || ky >= K) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          float wv[8];
+          load8(w + (size_t)(ky * K + kx) * C + c0, wv);
+#pragma unroll
+          for (int j = 0; j < SX; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][j][i] = fmaf(row[j * S + kx].get(i), wv[i], acc[r][j][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int oy = oy0 + r;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int j = 0; j < SX; ++j) {
+        const int ox = ox0 + j;
+        if (ox >= Wo) continue;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = silu<kExact>(acc[r][j][i] + sh[i]);
+          psum[i] += v[i];
+        }
+        store8(out_img + ((size_t)oy * Wo + ox) * C, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[tid * 8 + i] = psum[i];
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    const int o = c >> 3, ch = c & 7;
+    float s = 0.f;
+    for (int sl = 0; sl < spb; ++sl) s += part[(sl * n_oct + o) * 8 + ch];
+    pool_part[((size_t)img * gridDim.x + blockIdx.x) * C + c] = s;   // one writer per entry
+  }
+  if (se.wr == nullptr) return;
+
+  // ---- fused squeeze-excite (model.py:110-115), executed by the last block of this image
+  __shared__ int is_last;
+  __threadfence();                                 // publish this block's pool partials
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(se.counters + img, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid == 0) se.counters[img] = 0;              // leave the counter ready for the next launch
+  float* mean = part;                              // [C]   (dynamic smem is sized for max(blockDim*8, C+SQ))
+  float* sqv = part + C;                           // [SQ]
+  const int n_chunks = gridDim.x;
+  for (int c = tid; c < C; c += blockDim.x) {
+    double acc = 0.0;                              // fixed order, double: deterministic, as accurate as a mean
+    for (int j = 0; j < n_chunks; ++j) acc += (double)__ldcg(pool_part + ((size_t)img * n_chunks + j) * C + c);
+    mean[c] = (float)(acc * (double)se.inv_hw);
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;   // full warps only (shuffles)
+  for (int j = warp; j < se.sq && warp < nwarps; j += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(se.wr[(size_t)j * C + c], mean[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sqv[j] = silu<true>(s + se.br[j]);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = se.be[c];
+    for (int j = 0; j < se.sq; ++j) s = fmaf(se.we_t[(size_t)j * C + c], sqv[j], s);
+    se.gate[(size_t)img * C + c] = sigmoidf_<true>(s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SE excitation (model.py:110-115): mean = sum_chunks(pool_part)/hw; gate = sigmoid(We*swish(Wr*mean+br)+be).
+// One block handles kSeImgs images so the two small weight matrices are streamed from L2 once per
+// kSeImgs images; `we_t` is the expand weight transposed to [SQ][C] (lanes read consecutive channels).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSeImgs = 4;
 __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int n_chunks, float inv_hw,
                                                       const float* __restrict__ wr, const float* __restrict__ br,
-                                                      const float* __restrict__ we, const float* __restrict__ be,
-                                                      float* __restrict__ gate, int C, int SQ) {
+                                                      const float* __restrict__ we_t, const float* __restrict__ be,
+                                                      float* __restrict__ gate, int n_img, int C, int SQ) {
   extern __shared__ float sm[];
-  float* mean = sm;        // [C]
-  float* sq = sm + C;      // [SQ]
-  const int img = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double acc = 0.0;
-    for (int j = 0; j < n_chunks; ++j) acc += (double)pool_part[((size_t)img * n_chunks + j) * C + c];
-    mean[c] = (float)(acc * (double)inv_hw);
+  float* mean = sm;                  // [kSeImgs][C]
+  float* sq = sm + kSeImgs * C;      // [kSeImgs][SQ]
+  const int img0 = blockIdx.x * kSeImgs;
+  const int imgs = min(kSeImgs, n_img - img0);
+  for (int e = threadIdx.x; e < imgs * C; e += blockDim.x) {
+    const int i = e / C, c = e - i * C;
+    double acc = 0.0;                // fixed order, double: deterministic and as accurate as the reference's mean
+    for (int j = 0; j < n_chunks; ++j) acc += (double)pool_part[((size_t)(img0 + i) * n_chunks + j) * C + c];
+    mean[i * C + c] = (float)(acc * (double)inv_hw);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int j = warp; j < SQ; j += nwarps) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(wr[(size_t)j * C + c], mean[c], s);
+    float s[kSeImgs];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sq[j] = silu<true>(s + br[j]);
+    for (int i = 0; i < kSeImgs; ++i) s[i] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wv = wr[(size_t)j * C + c];
+#pragma unroll
+      for (int i = 0; i < kSeImgs; ++i)
+        if (i < imgs) s[i] = fmaf(wv, mean[i * C + c], s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kSeImgs; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+      if (lane == 0 && i < imgs) sq[i * SQ + j] = silu<true>(s[i] + br[j]);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = be[c];
-    for (int j = 0; j < SQ; ++j) s = fmaf(we[(size_t)c * SQ + j], sq[j], s);
-    gate[(size_t)img * C + c] = sigmoidf_<true>(s);
+    float s[kSeImgs];
+    const float bias = be[c];
+#pragma unroll
+    for (int i = 0; i < kSeImgs; ++i) s[i] = bias;
+    for (int j = 0; j < SQ; ++j) {
+      const float wv = we_t[(size_t)j * C + c];
+#pragma unroll
+      for (int i = 0; i < kSeImgs; ++i)
+        if (i < imgs) s[i] = fmaf(wv, sq[i * SQ + j], s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kSeImgs; ++i)
+      if (i < imgs) gate[(size_t)(img0 + i) * C + c] = sigmoidf_<true>(s[i]);
   }
 }
 
@@ -193,43 +341,63 @@ template <typename T, typename TIN>
 int launch_stem_t(const void* x, const float* w, const float* shift, void* out, int n_img, int H, int W,
                   cudaStream_t st) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const long long total = (long long)n_img * Ho * Wo * 4;
-  const int grid = (int)((total + 255) / 256);
+  const long long total = (long long)n_img * Ho * Wo;
+  const int grid = (int)((total + 127) / 128);
   ProfScope prof(st, 2.0 * 27 * 32 * (double)n_img * Ho * Wo,
                  (double)n_img * ((double)H * W * 3 * sizeof(TIN) + (double)Ho * Wo * 32 * sizeof(T)), "stem");
-  stem_kernel<T, TIN><<<grid, 256, 0, st>>>(reinterpret_cast<const TIN*>(x), w, shift, reinterpret_cast<T*>(out),
+  stem_kernel<T, TIN><<<grid, 128, 0, st>>>(reinterpret_cast<const TIN*>(x), w, shift, reinterpret_cast<T*>(out),
                                             n_img, H, W, Ho, Wo, same_pad_lo(H, 3, 2));
   MT_LAUNCH_CHECK("stem_kernel");
   return MT_OK;
 }
 
-template <typename T>
-int launch_dw_t(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
-                int C, int k, int s, cudaStream_t st) {
-  const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
-  dim3 grid((Ho * Wo + kDwPixPerBlock - 1) / kDwPixPerBlock, (C + 63) / 64, n_img);
-  const int pad = same_pad_lo(H, k, s);
-  const T* i = reinterpret_cast<const T*>(in);
-  T* o = reinterpret_cast<T*>(out);
-  ProfScope prof(st, 2.0 * k * k * (double)n_img * Ho * Wo * C,
-                 (double)n_img * C * ((double)H * W + (double)Ho * Wo) * sizeof(T), "dwconv k%d s%d C%d H%d", k, s, C, H);
-  if (k == 3 && s == 1) dwconv_kernel<T, 3, 1><<<grid, 256, 0, st>>>(i, w, shift, o, pool, H, W, Ho, Wo, C, pad);
-  else if (k == 3 && s == 2) dwconv_kernel<T, 3, 2><<<grid, 256, 0, st>>>(i, w, shift, o, pool, H, W, Ho, Wo, C, pad);
-  else if (k == 5 && s == 1) dwconv_kernel<T, 5, 1><<<grid, 256, 0, st>>>(i, w, shift, o, pool, H, W, Ho, Wo, C, pad);
-  else if (k == 5 && s == 2) dwconv_kernel<T, 5, 2><<<grid, 256, 0, st>>>(i, w, shift, o, pool, H, W, Ho, Wo, C, pad);
-  else {
-    set_error("dwconv: unsupported kernel %d / stride %d", k, s);
-    return MT_ERR_UNSUPPORTED;
-  }
+template <typename T, int K, int S>
+int launch_dw_ks(const T* i, const float* w, const float* shift, T* o, float* pool, int n_img, int H, int W, int C,
+                 const SeArgs& se, cudaStream_t st) {
+  const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
+  const DwGeom g = dw_geom(H, W, C, K, S);
+  dim3 grid(g.chunks, n_img);
+  const size_t smem = sizeof(float) * (size_t)std::max(g.threads * 8, C + se.sq);
+  dwconv_kernel<T, K, S><<<grid, g.threads, smem, st>>>(i, w, shift, o, pool, H, W, Ho, Wo, C, same_pad_lo(H, K, S),
+                                                        g.n_oct, g.spb, g.patches_x, g.patches, se);
   MT_LAUNCH_CHECK("dwconv_kernel");
   return MT_OK;
 }
 
+template <typename T>
+int launch_dw_t(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
+                int C, int k, int s, SeArgs se, cudaStream_t st) {
+  const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
+  const T* i = reinterpret_cast<const T*>(in);
+  T* o = reinterpret_cast<T*>(out);
+  se.inv_hw = 1.0f / (float)(Ho * Wo);
+  ProfScope prof(st, 2.0 * k * k * (double)n_img * Ho * Wo * C,
+                 (double)n_img * C * ((double)H * W + (double)Ho * Wo) * sizeof(T), "dwconv%s k%d s%d C%d H%d",
+                 se.wr ? "+se" : "", k, s, C, H);
+  if (k == 3 && s == 1) return launch_dw_ks<T, 3, 1>(i, w, shift, o, pool, n_img, H, W, C, se, st);
+  if (k == 3 && s == 2) return launch_dw_ks<T, 3, 2>(i, w, shift, o, pool, n_img, H, W, C, se, st);
+  if (k == 5 && s == 1) return launch_dw_ks<T, 5, 1>(i, w, shift, o, pool, n_img, H, W, C, se, st);
+  if (k == 5 && s == 2) return launch_dw_ks<T, 5, 2>(i, w, shift, o, pool, n_img, H, W, C, se, st);
+  set_error("dwconv: unsupported kernel %d / stride %d", k, s);
+  return MT_ERR_UNSUPPORTED;
+}
+
+int dwconv_dispatch(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
+                    int n_img, int h, int w_, int c, int k, int s, const SeArgs& se, cudaStream_t st) {
+  MT_REQUIRE(in && w && shift && out && pool_part, "dwconv: null pointer");
+  MT_REQUIRE(n_img > 0 && h > 0 && w_ > 0 && c >= 8 && c % 8 == 0 && c <= 2560,
+             "dwconv: bad shape n=%d h=%d w=%d c=%d (c %% 8 == 0)", n_img, h, w_, c);
+  MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
+  if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+  if (precision == MT_PREC_BF16) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+  set_error("dwconv: unknown precision %d", precision);
+  return MT_ERR_ARG;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int dw_chunks(int hw_out) { return (hw_out * hw_out + kDwPixPerBlock - 1) / kDwPixPerBlock; }
 
-struct BlockWs { size_t exp, dw, pool, gate, total; };
+struct BlockWs { size_t exp, dw, pool, gate, counters, total; };
 BlockWs block_ws_layout(const mt_mbconv_spec_t& b, int n_img, int precision) {
   const size_t es = precision == MT_PREC_FP32 ? 4 : 2;
   const size_t ho = (b.hw_in + b.stride - 1) / b.stride, cexp = (size_t)b.cin * b.expand;
@@ -237,8 +405,9 @@ BlockWs block_ws_layout(const mt_mbconv_spec_t& b, int n_img, int precision) {
   size_t off = 0;
   l.exp = off;  off += b.expand != 1 ? align_up((size_t)b.hw_in * b.hw_in * cexp * n_img * es, 1024) : 0;
   l.dw = off;   off += align_up(ho * ho * cexp * n_img * es, 1024);
-  l.pool = off; off += align_up((size_t)dw_chunks((int)ho) * cexp * n_img * 4, 1024);
+  l.pool = off; off += align_up((size_t)dw_geom(b.hw_in, b.hw_in, (int)cexp, b.kernel, b.stride).chunks * cexp * n_img * 4, 1024);
   l.gate = off; off += align_up(cexp * n_img * 4, 1024);
+  l.counters = off; off += align_up((size_t)n_img * 4, 1024);
   l.total = off;
   return l;
 }
@@ -288,32 +457,39 @@ extern "C" int mt_stem_fwd(int precision, const void* x, int x_dtype, const floa
   return MT_ERR_ARG;
 }
 
-extern "C" int mt_dwconv_chunks(int h, int w_, int s) {
-  if (h <= 0 || w_ <= 0 || s <= 0) return 0;
-  return (((h + s - 1) / s) * ((w_ + s - 1) / s) + kDwPixPerBlock - 1) / kDwPixPerBlock;
+extern "C" int mt_dwconv_chunks(int h, int w_, int c, int k, int s) {
+  if (h <= 0 || w_ <= 0 || c < 8 || c % 8 != 0 || (s != 1 && s != 2) || (k != 3 && k != 5)) return 0;
+  return dw_geom(h, w_, c, k, s).chunks;
 }
 
 extern "C" int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out,
                              float* pool_part, int n_img, int h, int w_, int c, int k, int s, void* stream) {
-  MT_REQUIRE(in && w && shift && out && pool_part, "dwconv: null pointer");
-  MT_REQUIRE(n_img > 0 && h > 0 && w_ > 0 && c > 0 && c % 2 == 0, "dwconv: bad shape n=%d h=%d w=%d c=%d", n_img, h, w_, c);
-  MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, st);
-  if (precision == MT_PREC_BF16) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, st);
-  set_error("dwconv: unknown precision %d", precision);
-  return MT_ERR_ARG;
+  SeArgs se{};
+  return dwconv_dispatch(precision, in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mt_dwconv_se_fwd(int precision, const void* in, const float* w, const float* shift, void* out,
+                                float* pool_part, int* counters, const float* wr, const float* br, const float* we_t,
+                                const float* be, float* gate, int n_img, int h, int w_, int c, int k, int s, int sq,
+                                void* stream) {
+  MT_REQUIRE(counters && wr && br && we_t && be && gate && sq > 0, "dwconv_se: null pointer / bad squeeze width");
+  SeArgs se{};
+  se.wr = wr; se.br = br; se.we_t = we_t; se.be = be; se.gate = gate; se.counters = counters; se.sq = sq;
+  return dwconv_dispatch(precision, in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br,
                               const float* we, const float* be, float* gate, int n_img, int c, int sq, void* stream) {
   MT_REQUIRE(pool_part && wr && br && we && be && gate, "se_gate: null pointer");
-  MT_REQUIRE(n_img > 0 && c > 0 && sq > 0 && hw > 0 && n_chunks > 0 && (size_t)(c + sq) * 4 <= 48 * 1024,
+  MT_REQUIRE(n_img > 0 && c > 0 && sq > 0 && hw > 0 && n_chunks > 0 && (size_t)(c + sq) * 4 * kSeImgs <= 48 * 1024,
              "se_gate: bad shape");
   ProfScope prof(reinterpret_cast<cudaStream_t>(stream), 4.0 * n_img * (double)c * sq,
                  (double)n_img * c * 4 * (n_chunks + 1), "se_gate");
-  se_gate_kernel<<<n_img, 256, (size_t)(c + sq) * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
-      pool_part, n_chunks, 1.0f / (float)hw, wr, br, we, be, gate, c, sq);
+  se_gate_kernel<<<(n_img + kSeImgs - 1) / kSeImgs, 256, (size_t)(c + sq) * 4 * kSeImgs,
+                   reinterpret_cast<cudaStream_t>(stream)>>>(pool_part, n_chunks, 1.0f / (float)hw, wr, br, we, be, gate,
+                                                             n_img, c, sq);
   MT_LAUNCH_CHECK("se_gate_kernel");
   return MT_OK;
 }
@@ -374,11 +550,12 @@ extern "C" int mt_mbconv_fwd(int precision, const mt_mbconv_spec_t* spec, const 
     if (rc) return rc;
     dw_in = bexp;
   }
-  rc = mt_dwconv_fwd(precision, dw_in, w->dw_w, w->dw_shift, bdw, pool, n_img, b.hw_in, b.hw_in, cexp, b.kernel,
-                     b.stride, stream);
-  if (rc) return rc;
-  rc = mt_se_gate_fwd(pool, dw_chunks(ho), ho * ho, w->se_reduce_w, w->se_reduce_b, w->se_expand_w, w->se_expand_b,
-                      gate, n_img, cexp, sq, stream);
+  int* counters = reinterpret_cast<int*>(ws + l.counters);
+  cudaError_t ce = cudaMemsetAsync(counters, 0, (size_t)n_img * sizeof(int), reinterpret_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return cuda_status(ce, "cudaMemsetAsync(se counters)");
+  rc = mt_dwconv_se_fwd(precision, dw_in, w->dw_w, w->dw_shift, bdw, pool, counters, w->se_reduce_w, w->se_reduce_b,
+                        w->se_expand_w, w->se_expand_b, gate, n_img, b.hw_in, b.hw_in, cexp, b.kernel, b.stride, sq,
+                        stream);
   if (rc) return rc;
   const bool skip = b.stride == 1 && b.cin == b.cout;   // model.py:123
   return mt_pointwise_fwd(precision, bdw, w->project.w, w->project.shift, gate, ho * ho, skip ? in : nullptr, 0, out,

@@ -2,10 +2,15 @@
 // (reference model.py:101,118,286 via utils.py:273-276) and every nn.Linear of the TimeSformer
 // (size_invariant_timesformer.py:68-73,102-106,175).
 //
-//  * gemm_tc_kernel   (bf16): TMA-staged 128 x block_n x 64 tiles (128-byte swizzle), tcgen05.mma with
-//    fp32 accumulators in TMEM (double buffered), warp-specialised: 1 TMA producer warp, 1 MMA issuer
-//    warp, 4 epilogue warps (tcgen05.ld -> fused epilogue -> global), + 4 "gate" warps when the A
-//    operand carries the squeeze-excite scale.  Persistent over output tiles.
+//  * gemm_tc_kernel (bf16): persistent, warp-specialised tcgen05 GEMM.
+//      warp 0      TMA producer: A (128 x 64) and W (block_n x 64) tiles, 128-byte swizzle, mbarrier ring
+//      warp 1      MMA issuer: tcgen05.mma kind::f16, fp32 accumulators in TMEM, double buffered
+//      warps 2-5   epilogue: tcgen05.ld -> bias / swish / GEGLU in registers -> swizzled smem staging ->
+//                  TMA store (bf16) or TMA reduce-add (fp32 residual stream), double buffered, so global
+//                  writes are full 128-byte lines issued by the copy engine instead of per-row stores
+//      warps 6-9   (GATED only) scale the landed A tile by the squeeze-excite gate before the MMA reads it
+//    The direct-store epilogue (TMA_OUT = false) is kept for the two cases that need per-row gathers:
+//    the MBConv skip connection and the patch-embedding (+pos/size embedding rows).
 //  * gemm_simt_kernel (fp32 / any T): plain FFMA tiles with the same epilogues -- the exact path.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -16,20 +21,18 @@
 #include "ptx.cuh"
 
 namespace mt {
-
-// =====================================================================================================
-// tcgen05 kernel
-// =====================================================================================================
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                       // 64 bf16 = one 128-byte swizzle row
+constexpr int kBlockK = 64;                          // 64 bf16 = one 128-byte swizzle row
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
+constexpr int kStagingBytes = kBlockM * 128;         // one epilogue staging buffer: 128 rows x 128 B
+constexpr int kEpiThread0 = 64;                      // first epilogue thread (warp 2, lane 0)
 
 struct TcParams {
   int M, N, K;
-  int block_n;      // multiple of 16, <= 256 (multiple of 64 for GEGLU)
+  int block_n;      // multiple of 16, <= 256 (multiple of 128 for GEGLU)
   int stages;
   int tiles_m, tiles_n;
   int tmem_cols;    // power of two >= 2 * block_n
@@ -46,16 +49,45 @@ struct PipeState {
   }
 };
 
-template <typename T, int KIND, bool GATED>
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 2 MUFU + ~10 FMA instead of erff's ~25
+// instructions -- the GEGLU epilogue evaluates 128 of them per thread per tile.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float fast_gelu(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// staging buffer = 128 rows of 128 B with the TMA 128-byte swizzle: 16-byte piece p of row r lives at
+// r*128 + ((p ^ (r & 7)) << 4)  (conflict-free for a warp writing 32 different rows)
+__device__ __forceinline__ uint4* staging_piece(uint8_t* buf, int row, int piece) {
+  return reinterpret_cast<uint4*>(buf + row * 128 + ((piece ^ (row & 7)) << 4));
+}
+
+template <typename T, int KIND, bool GATED, bool TMA_OUT>
 __global__ void __launch_bounds__(GATED ? 320 : 192, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up: [A stages][B stages][barriers][tmem ptr]
+  // carve-up: [A stages][B stages][2 staging buffers (TMA_OUT)][barriers][tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage_bytes = p.block_n * kBlockK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages * kAStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage_bytes);
+  uint8_t* smem_stage = smem_b + p.stages * b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + (TMA_OUT ? 2 * kStagingBytes : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* gated_bar = bars + 2 * kMaxStages;
@@ -69,6 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (TMA_OUT) ptx::prefetch_tmap(&tmap_out);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -144,76 +177,140 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp < 6) {
     // ===================================================================== epilogue (4 warps)
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int trow = quad * 32 + lane;             // row of the tile this thread owns
+    const EpiParams& e = p.epi;
+    uint32_t store_it = 0;                         // staging buffer ring position (TMA_OUT)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / p.tiles_n) * kBlockM;
       const int n0 = (tile % p.tiles_n) * p.block_n;
-      const int row = m0 + quad * 32 + lane;
+      const int row = m0 + trow;
       const bool row_ok = row < p.M;
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
-      if (KIND == EPI_GEGLU) {
-        for (int c = 0; c < p.block_n; c += 64) {
-          uint32_t ru[32], rg[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c, ru);
-          ptx::tmem_ld_32x32b_x32(taddr + c + 32, rg);
-          ptx::tmem_ld_wait();
-          if (row_ok) {
+
+      if (TMA_OUT) {
+        // accumulator columns consumed per staging buffer: 64 (bf16 store), 128 (GEGLU -> 64 outputs),
+        // 32 (fp32 reduce-add); each fills 128 B per row
+        constexpr int kChunk = KIND == EPI_GEGLU ? 128 : (KIND == EPI_RESID_F32 ? 32 : 64);
+        for (int c = 0; c < p.block_n; c += kChunk) {
+          uint8_t* stg = smem_stage + (store_it & 1) * kStagingBytes;
+          if (threadIdx.x == kEpiThread0)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer's previous store drained
+          bar_sync_epi();
+          if (KIND == EPI_GEGLU) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = n0 + c + g * 8;
-              if (col < p.N) {
+            for (int ob = 0; ob < 2; ++ob) {        // two 64-wide interleave blocks: [32 u | 32 gate]
+              uint32_t ru[32], rg[32];
+              ptx::tmem_ld_32x32b_x32(taddr + c + ob * 64, ru);
+              ptx::tmem_ld_32x32b_x32(taddr + c + ob * 64 + 32, rg);
+              ptx::tmem_ld_wait();
+              const int col = n0 + c + ob * 64;     // packed column of u[0]
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
                 float u[8], gg[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { u[i] = __uint_as_float(ru[g * 8 + i]); gg[i] = __uint_as_float(rg[g * 8 + i]); }
-                epi_geglu8<T>(p.epi, row, col, u, gg);
-              }
-            }
-          }
-        }
-      } else {
-        for (int c = 0; c < p.block_n; c += 32) {
-          if (p.block_n - c >= 32) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(taddr + c, r);
-            ptx::tmem_ld_wait();
-            if (row_ok) {
+                if (e.bias && col + 64 <= p.N) {
+                  float b[8];
+                  load8(e.bias + col + g * 8, b);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int col = n0 + c + g * 8;
-                if (col < p.N) {
-                  float v[8];
+                  for (int i = 0; i < 8; ++i) u[i] += b[i];
+                  load8(e.bias + col + 32 + g * 8, b);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                  epi_store8<T, KIND>(p.epi, row, col, v);
+                  for (int i = 0; i < 8; ++i) gg[i] += b[i];
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[i] *= fast_gelu(gg[i]);
+                *staging_piece(stg, trow, ob * 4 + g) =
+                    make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
               }
             }
           } else {
-            uint32_t r[16];
-            ptx::tmem_ld_32x32b_x16(taddr + c, r);
+            constexpr int kQ = kChunk / 16;         // 16-column quarters in this chunk
+            uint32_t r[kQ][16];
+#pragma unroll
+            for (int q = 0; q < kQ; ++q)
+              if (c + q * 16 < p.block_n) ptx::tmem_ld_32x32b_x16(taddr + c + q * 16, r[q]);
             ptx::tmem_ld_wait();
-            if (row_ok) {
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const int col = n0 + c + g * 8;
-                if (col < p.N) {
-                  float v[8];
+            for (int q = 0; q < kQ; ++q) {
+              if (c + q * 16 >= p.block_n) continue;
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                  epi_store8<T, KIND>(p.epi, row, col, v);
+              for (int hh = 0; hh < 2; ++hh) {
+                const int col = n0 + c + q * 16 + hh * 8;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q][hh * 8 + i]);
+                if (e.bias && col < p.N) {
+                  float b[8];
+                  load8(e.bias + col, b);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] += b[i];
+                }
+                if (KIND == EPI_STORE) {
+                  if (e.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = silu<false>(v[i]);
+                  }
+                  *staging_piece(stg, trow, q * 2 + hh) =
+                      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                } else {                            // EPI_RESID_F32: 8 fp32 = two 16-byte pieces
+                  *staging_piece(stg, trow, q * 4 + hh * 2) =
+                      make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                  *staging_piece(stg, trow, q * 4 + hh * 2 + 1) =
+                      make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
                 }
               }
             }
           }
+          if (c + kChunk >= p.block_n) {            // last TMEM read of this tile: hand the accumulator back
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tmem_empty[as]);
+          }
+          ptx::fence_proxy_async_smem();            // staging writes -> visible to the TMA engine
+          bar_sync_epi();
+          if (threadIdx.x == kEpiThread0) {
+            const int ocol = KIND == EPI_GEGLU ? (n0 + c) / 2 : n0 + c;
+            if (KIND == EPI_RESID_F32)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(ptx::smem_u32(stg)), "r"(ocol), "r"(m0)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(ptx::smem_u32(stg)), "r"(ocol), "r"(m0)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++store_it;
         }
+      } else {
+        // ------------------------------------------------------------- direct (per-row) stores
+        for (int c = 0; c < p.block_n; c += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(taddr + c, r);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int col = n0 + c + g * 8;
+              if (col < p.N) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                epi_store8<T, KIND>(e, row, col, v);
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[as]);
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty[as]);
     }
+    if (TMA_OUT && threadIdx.x == kEpiThread0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (GATED) {
     // ===================================================================== SE-gate warps (4 warps)
     // Multiply the freshly landed A tile by gate[image(row)][k] in shared memory (reference
@@ -366,22 +463,25 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 row-major [rows][cols] tensor, box = [box_rows][64 cols], 128-byte swizzle, zero OOB fill.
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+// 2D row-major [rows][cols] tensor (row pitch = pitch_elems), box = [box_rows][128 bytes of columns],
+// 128-byte swizzle, zero fill / clipping out of bounds.
+int make_tmap_2d(CUtensorMap* m, const void* base, bool f32, int rows, int cols, int pitch_elems, int box_rows) {
   auto enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return MT_ERR_DRIVER;
   }
+  const int es = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box_rows=%d base=%p", (int)r, rows, cols, box_rows, base);
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d pitch=%d box_rows=%d base=%p", (int)r, rows, cols,
+              pitch_elems, box_rows, base);
     return MT_ERR_DRIVER;
   }
   return MT_OK;
@@ -398,19 +498,21 @@ int num_sms() {
   return n;
 }
 
-template <int KIND, bool GATED>
-int launch_tc(const GemmArgs& g, cudaStream_t stream) {
+template <int KIND, bool GATED, bool TMA_OUT>
+int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.gate = g.gate; p.rows_per_gate = g.rows_per_gate;
   p.epi = g.epi;
-  // tile width: whole N if it fits one UMMA (<= 256), else 256 / 128 so that the tile count divides well
   int bn;
   if (KIND == EPI_GEGLU) {
     bn = 256;
   } else {
-    const int parts = (g.N + 255) / 256;            // fewest UMMA-wide (<= 256) column tiles ...
+    const int parts = (g.N + 255) / 256;              // fewest UMMA-wide (<= 256) column tiles ...
     bn = ((g.N + parts - 1) / parts + 15) / 16 * 16;  // ... of equal width (multiple of 16)
+    // several column tiles: a TMA store box is 128 B wide, so tiles must start on 64-column boundaries
+    // (a partial last box of tile i would otherwise spill stale staging data into tile i+1's columns)
+    if (parts > 1) bn = (bn + 63) / 64 * 64;
   }
   p.block_n = bn;
   p.tiles_m = (g.M + kBlockM - 1) / kBlockM;
@@ -419,32 +521,51 @@ int launch_tc(const GemmArgs& g, cudaStream_t stream) {
   while (tmem < 2 * bn) tmem <<= 1;
   p.tmem_cols = tmem;
   const int stage_bytes = kAStageBytes + bn * kBlockK * 2;
-  const int budget = (bn <= 128 ? 100 : 200) * 1024;   // <=128-wide tiles: leave room for 2 CTAs / SM
+  const int fixed = (TMA_OUT ? 2 * kStagingBytes : 0) + 1024 /*align slack*/ + (3 * kMaxStages + 4) * 8 + 16;
+  // <=128-wide tiles leave room for 2 CTAs per SM (2 x (112 KiB + 1 KiB reserved) <= 228 KiB)
+  const int ctas_per_sm = bn <= 128 ? 2 : 1;
+  const int budget = (ctas_per_sm == 2 ? 112 : 226) * 1024 - fixed;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (3 * kMaxStages + 4) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
 
-  CUtensorMap ta, tb;
-  int rc = make_tmap_bf16(&ta, g.a, g.M, g.K, kBlockM);
+  CUtensorMap ta, tb, tout;
+  int rc = make_tmap_2d(&ta, g.a, false, g.M, g.K, g.K, kBlockM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, g.w, g.N, g.K, bn);
+  rc = make_tmap_2d(&tb, g.w, false, g.N, g.K, g.K, bn);
   if (rc) return rc;
+  if (TMA_OUT) {
+    const bool f32 = KIND == EPI_RESID_F32;
+    const int out_cols = KIND == EPI_GEGLU ? g.N / 2 : g.N;
+    rc = make_tmap_2d(&tout, g.epi.out, f32, g.M, out_cols, g.epi.ldo, kBlockM);
+    if (rc) return rc;
+  } else {
+    tout = ta;
+  }
 
-  auto kern = gemm_tc_kernel<bf16, KIND, GATED>;
+  auto kern = gemm_tc_kernel<bf16, KIND, GATED, TMA_OUT>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc)");
     attr_set = true;
   }
-  const int ctas_per_sm = bn <= 128 ? 2 : 1;
   int grid = p.tiles_m * p.tiles_n;
   if (grid > num_sms() * ctas_per_sm) grid = num_sms() * ctas_per_sm;
-  kern<<<grid, GATED ? 320 : 192, smem, stream>>>(ta, tb, p);
+  kern<<<grid, GATED ? 320 : 192, smem, stream>>>(ta, tb, tout, p);
   MT_LAUNCH_CHECK("gemm_tc_kernel");
   return MT_OK;
+}
+
+template <int KIND, bool GATED>
+int launch_tc(const GemmArgs& g, cudaStream_t stream) {
+  // per-row gathers (skip connection, embedding rows) use the direct epilogue; everything else TMA
+  if (KIND == EPI_PATCH_EMBED || (KIND == EPI_STORE && g.epi.resid)) return launch_tc_impl<KIND, GATED, false>(g, stream);
+  if ((g.epi.ldo * (KIND == EPI_RESID_F32 ? 4 : 2)) % 16 != 0 || (reinterpret_cast<uintptr_t>(g.epi.out) & 15))
+    return launch_tc_impl<KIND, GATED, false>(g, stream);
+  return launch_tc_impl<KIND, GATED, true>(g, stream);
 }
 
 template <typename T, int KIND, bool GATED>
@@ -490,7 +611,7 @@ int launch_gemm(int precision, const GemmArgs& g, cudaStream_t stream) {
       MT_REQUIRE(!gated, "gemm: gate unsupported for this epilogue");
       return dispatch_prec<EPI_RESID_F32, false>(precision, g, stream);
     case EPI_GEGLU:
-      MT_REQUIRE(!gated && g.N % 64 == 0, "gemm: GEGLU needs N %% 64 == 0 (N=%d)", g.N);
+      MT_REQUIRE(!gated && g.N % 128 == 0, "gemm: GEGLU needs N %% 128 == 0 (N=%d)", g.N);
       return dispatch_prec<EPI_GEGLU, false>(precision, g, stream);
     case EPI_PATCH_EMBED:
       MT_REQUIRE(!gated, "gemm: gate unsupported for this epilogue");

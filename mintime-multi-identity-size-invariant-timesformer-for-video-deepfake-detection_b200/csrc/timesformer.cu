@@ -4,6 +4,9 @@
 // layer schedule.  Residual stream x is fp32 [B][1+f*n][dim]; GEMM operands are T.
 #include <float.h>
 
+#include <type_traits>
+
+#include "attention_mma.cuh"
 #include "common.cuh"
 
 namespace mt {
@@ -282,6 +285,30 @@ int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, i
   const double gq = mode == MT_ATTN_TIME ? f : n, groups = (double)B * heads * (mode == MT_ATTN_TIME ? n : f);
   ProfScope prof(st, 4.0 * groups * 64.0 * gq * (gq + 1), (double)B * N * heads * 64 * 4 * sizeof(T),
                  mode == MT_ATTN_TIME ? "attn_time" : "attn_space");
+  if constexpr (std::is_same<T, bf16>::value) {
+    // bf16 path: warp-level tensor-core kernels (attention_mma.cuh)
+    if (mode == MT_ATTN_SPACE) {
+      attn::attn_space_mma_kernel<<<B * heads * f, 128, 0, st>>>(q, o, f, n, heads);
+      MT_LAUNCH_CHECK("attn_space_mma_kernel");
+      return MT_OK;
+    }
+    const int grid = B * heads * ((n + 3) / 4);
+    auto launch_time = [&](auto kern, int nkt, int mt_) -> int {
+      const size_t dyn = 4 * (size_t)(mt_ * 16 * 128 + 2 * nkt * 16 * 128);
+      if (dyn > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(attn_time)");
+      }
+      kern<<<grid, 128, dyn, st>>>(q, mask, idmask, o, f, n, heads);
+      MT_LAUNCH_CHECK("attn_time_mma_kernel");
+      return MT_OK;
+    };
+    if (f <= 15) return launch_time(attn::attn_time_mma_kernel<1, 1>, 1, 1);
+    if (f == 16) return launch_time(attn::attn_time_mma_kernel<2, 1>, 2, 1);
+    if (f <= 31) return launch_time(attn::attn_time_mma_kernel<2, 2>, 2, 2);
+    if (f == 32) return launch_time(attn::attn_time_mma_kernel<3, 2>, 3, 2);
+    // other frame counts: generic kernel below
+  }
   if (mode == MT_ATTN_TIME)
     attn_group_kernel<T, MT_ATTN_TIME><<<B * heads * n, 128, 0, st>>>(q, mask, idmask, o, f, n, heads);
   else

@@ -77,7 +77,7 @@ def pack_effnet(sd: Dict[str, torch.Tensor], precision: str, device) -> Packed:
         blk.dw_shift = pk.p(shift, f32, device)
         blk.se_reduce_w = pk.p(sd[p + "_se_reduce.weight"].flatten(1), f32, device)
         blk.se_reduce_b = pk.p(sd[p + "_se_reduce.bias"], f32, device)
-        blk.se_expand_w = pk.p(sd[p + "_se_expand.weight"].flatten(1), f32, device)
+        blk.se_expand_w = pk.p(sd[p + "_se_expand.weight"].flatten(1).t(), f32, device)     # [sq][cexp]
         blk.se_expand_b = pk.p(sd[p + "_se_expand.bias"], f32, device)
         blk.project = pw(p + "_project_conv.weight", p + "_bn2")
     W.head = pw("_conv_head.weight", "_bn1")
