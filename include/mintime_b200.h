@@ -172,9 +172,10 @@ int mt_stem_fwd(int precision, const void* x, int x_dtype, const float* w, const
 
 /* Depthwise kxk stride s conv with TF-SAME padding + BN + swish, plus partial sums for the SE squeeze
  * (model.py:105-107,110): in T NHWC [n_img][h][w][c] -> out T NHWC [n_img][ceil(h/s)][ceil(w/s)][c];
- * pool_part f32 [n_img][n_chunks][c], n_chunks = mt_dwconv_chunks(h, w, c, k, s): sum of out over each chunk
- * of output pixels (every entry is written; no zero-init; deterministic -- no atomics). */
-int mt_dwconv_chunks(int h, int w_, int c, int k, int s);
+ * pool_part f32 [n_img][n_chunks][c], n_chunks = mt_dwconv_chunks(precision, h, w, c, k, s): sum of out over
+ * each chunk (spatial tile) of output pixels (every entry is written; no zero-init; no atomics: deterministic).
+ * bf16 path: tensor-core kernel (TMA-staged NHWC tile, block-diagonal mma.sync); fp32 path: FFMA kernel. */
+int mt_dwconv_chunks(int precision, int h, int w_, int c, int k, int s);
 int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
                   int n_img, int h, int w_, int c, int k, int s, void* stream);
 

@@ -101,7 +101,7 @@ def load() -> C.CDLL:
     lib.mt_stem_fwd.argtypes = [i32, vp, i32, fp, fp, vp, i32, i32, i32, vp]
     lib.mt_dwconv_fwd.argtypes = [i32, vp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_se_gate_fwd.argtypes = [fp, i32, i32, fp, fp, fp, fp, fp, i32, i32, i32, vp]
-    lib.mt_dwconv_chunks.argtypes = [i32, i32, i32, i32, i32]
+    lib.mt_dwconv_chunks.argtypes = [i32, i32, i32, i32, i32, i32]
     lib.mt_dwconv_se_fwd.argtypes = [i32, vp, fp, fp, vp, fp, vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_dwconv_chunks.restype = i32
     lib.mt_effnet_b0_block_spec.argtypes = [i32, C.POINTER(MBConvSpec)]

@@ -129,7 +129,7 @@ __device__ __forceinline__ void attend_mtile(uint8_t* qs, uint8_t* ks, uint8_t* 
 // ---------------------------------------------------------------------------------------------------
 // SPACE: one block (4 warps) per group (b, h, frame): 49 queries x (CLS + 49) keys, no mask (:266).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attn_space_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int f,
+static __global__ void __launch_bounds__(128) attn_space_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int f,
                                                              int n, int heads) {
   __shared__ __align__(1024) uint8_t sm[3 * 64 * 128];
   uint8_t* qs = sm;

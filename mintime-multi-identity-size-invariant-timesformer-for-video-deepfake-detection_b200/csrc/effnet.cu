@@ -5,6 +5,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "dwconv_tc.cuh"
 
 namespace mt {
 namespace {
@@ -139,19 +140,12 @@ inline DwGeom dw_geom(int H, int W, int C, int k, int s) {
   return g;
 }
 
-// Squeeze-excite tail fused into the depthwise kernel: the LAST block to finish an image (per-image
+// Squeeze-excite tail fused into the depthwise kernels: the LAST block to finish an image (per-image
 // arrival counter) reduces that image's pool partials and runs the two tiny FC layers, so the SE gate
 // costs no extra launch and overlaps with the depthwise work of the other images.
-struct SeArgs {
-  const float* wr;    // [SQ][C]   (null: no fused SE)
-  const float* br;    // [SQ]
-  const float* we_t;  // [SQ][C]
-  const float* be;    // [C]
-  float* gate;        // [n_img][C]
-  int* counters;      // [n_img], zero on entry, zero again on exit
-  int sq;
-  float inv_hw;
-};
+//   wr [SQ][C] (null: no fused SE), br [SQ], we_t [SQ][C], be [C], gate [n_img][C],
+//   counters [n_img] zero on entry / zero again on exit.
+using SeArgs = DwSeArgs;
 
 template <typename T, int K, int S>
 __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
@@ -382,6 +376,55 @@ int launch_dw_t(const void* in, const float* w, const float* shift, void* out, f
   return MT_ERR_UNSUPPORTED;
 }
 
+template <int K, int S>
+int launch_dw_tc_ks(const CUtensorMap& tm, const float* w, const float* shift, bf16* o, float* pool, int n_img, int H,
+                    int W, int C, const DwTcGeom& g, const SeArgs& se, cudaStream_t st) {
+  const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
+  auto kern = dwconv_tc_kernel<K, S>;
+  const size_t smem = (size_t)std::max(g.tile_bytes, (C + se.sq) * 4) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(dwconv_tc)");
+    attr_set = true;
+  }
+  dim3 grid(g.tiles_x * g.tiles_y, g.n_cchunks, n_img);
+  kern<<<grid, 256, smem, st>>>(tm, w, shift, o, pool, Ho, Wo, C, same_pad_lo(H, K, S), g, se);
+  MT_LAUNCH_CHECK("dwconv_tc_kernel");
+  return MT_OK;
+}
+
+int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
+                 int C, int k, int s, SeArgs se, cudaStream_t st) {
+  if ((k != 3 && k != 5) || (s != 1 && s != 2)) {
+    set_error("dwconv: unsupported kernel %d / stride %d", k, s);
+    return MT_ERR_UNSUPPORTED;
+  }
+  const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
+  const DwTcGeom g = dw_tc_geom(H, W, C, k, s);
+  MT_REQUIRE(g.IW <= 256 && g.IH <= 256 && g.tile_bytes <= 62 * 1024, "dwconv: tile too large (%dx%d)", g.IW, g.IH);
+  CUtensorMap tm;
+  int rc = make_tmap_nhwc_bf16(&tm, in, n_img, H, W, C, g.IW, g.IH);
+  if (rc) return rc;
+  se.inv_hw = 1.0f / (float)(Ho * Wo);
+  ProfScope prof(st, 2.0 * k * k * (double)n_img * Ho * Wo * C,
+                 (double)n_img * C * ((double)H * W + (double)Ho * Wo) * 2, "dwconv_tc%s k%d s%d C%d H%d",
+                 se.wr ? "+se" : "", k, s, C, H);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if (k == 3 && s == 1) return launch_dw_tc_ks<3, 1>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
+  if (k == 3 && s == 2) return launch_dw_tc_ks<3, 2>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
+  if (k == 5 && s == 1) return launch_dw_tc_ks<5, 1>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
+  return launch_dw_tc_ks<5, 2>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
+}
+
+int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
+  if (precision == MT_PREC_BF16) {
+    const DwTcGeom g = dw_tc_geom(h, w_, c, k, s);
+    return g.tiles_x * g.tiles_y;
+  }
+  return dw_geom(h, w_, c, k, s).chunks;
+}
+
 int dwconv_dispatch(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
                     int n_img, int h, int w_, int c, int k, int s, const SeArgs& se, cudaStream_t st) {
   MT_REQUIRE(in && w && shift && out && pool_part, "dwconv: null pointer");
@@ -389,7 +432,8 @@ int dwconv_dispatch(int precision, const void* in, const float* w, const float* 
              "dwconv: bad shape n=%d h=%d w=%d c=%d (c %% 8 == 0)", n_img, h, w_, c);
   MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
   if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
-  if (precision == MT_PREC_BF16) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+  if (precision == MT_PREC_BF16) return launch_dw_tc(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+  if (precision == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);  // debug: CUDA-core bf16
   set_error("dwconv: unknown precision %d", precision);
   return MT_ERR_ARG;
 }
@@ -405,7 +449,7 @@ BlockWs block_ws_layout(const mt_mbconv_spec_t& b, int n_img, int precision) {
   size_t off = 0;
   l.exp = off;  off += b.expand != 1 ? align_up((size_t)b.hw_in * b.hw_in * cexp * n_img * es, 1024) : 0;
   l.dw = off;   off += align_up(ho * ho * cexp * n_img * es, 1024);
-  l.pool = off; off += align_up((size_t)dw_geom(b.hw_in, b.hw_in, (int)cexp, b.kernel, b.stride).chunks * cexp * n_img * 4, 1024);
+  l.pool = off; off += align_up((size_t)dw_chunks(precision, b.hw_in, b.hw_in, (int)cexp, b.kernel, b.stride) * cexp * n_img * 4, 1024);
   l.gate = off; off += align_up(cexp * n_img * 4, 1024);
   l.counters = off; off += align_up((size_t)n_img * 4, 1024);
   l.total = off;
@@ -457,9 +501,9 @@ extern "C" int mt_stem_fwd(int precision, const void* x, int x_dtype, const floa
   return MT_ERR_ARG;
 }
 
-extern "C" int mt_dwconv_chunks(int h, int w_, int c, int k, int s) {
+extern "C" int mt_dwconv_chunks(int precision, int h, int w_, int c, int k, int s) {
   if (h <= 0 || w_ <= 0 || c < 8 || c % 8 != 0 || (s != 1 && s != 2) || (k != 3 && k != 5)) return 0;
-  return dw_geom(h, w_, c, k, s).chunks;
+  return dw_chunks(precision, h, w_, c, k, s);
 }
 
 extern "C" int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out,

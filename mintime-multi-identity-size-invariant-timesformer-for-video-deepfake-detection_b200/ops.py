@@ -121,7 +121,7 @@ def dwconv(x_nhwc, w_taps, shift, k: int, s: int, precision="bf16"):
     _lib.require_device(x_nhwc.device)
     lib = _lib.load()
     out = torch.empty((n, (h + s - 1) // s, (w + s - 1) // s, c), dtype=T, device=x_nhwc.device)
-    pool = torch.full((n, lib.mt_dwconv_chunks(h, w, c, k, s), c), float("nan"), dtype=torch.float32,
+    pool = torch.full((n, lib.mt_dwconv_chunks(_lib.prec_id(precision), h, w, c, k, s), c), float("nan"), dtype=torch.float32,
                       device=x_nhwc.device)
     with torch.cuda.device(x_nhwc.device):
         rc = lib.mt_dwconv_fwd(_lib.prec_id(precision), x_nhwc.data_ptr(), w_taps.data_ptr(), shift.data_ptr(),
@@ -141,7 +141,8 @@ def dwconv_se(x_nhwc, w_taps, shift, k: int, s: int, wr, br, we_t, be, precision
     lib = _lib.load()
     dev = x_nhwc.device
     out = torch.empty((n, (h + s - 1) // s, (w + s - 1) // s, c), dtype=T, device=dev)
-    pool = torch.empty((n, lib.mt_dwconv_chunks(h, w, c, k, s), c), dtype=torch.float32, device=dev)
+    pool = torch.empty((n, lib.mt_dwconv_chunks(_lib.prec_id(precision), h, w, c, k, s), c), dtype=torch.float32,
+                       device=dev)
     counters = torch.zeros((n,), dtype=torch.int32, device=dev)
     gate = torch.full((n, c), float("nan"), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):

@@ -208,7 +208,8 @@ def test_dwconv_swish_pool(prec, k, s, h, c):
     torch.cuda.synchronize()
     assert out.shape == (n, (h + s - 1) // s, (h + s - 1) // s, c)
     assert rel_err(out.float().cpu().permute(0, 3, 1, 2), ref) <= tol(prec, 1e-5, 4e-3)
-    assert rel_err(pool.cpu().sum(1), ref.sum((2, 3))) <= tol(prec, 1e-5, 1e-4)     # pooled before bf16 rounding
+    # pooled before the bf16 rounding of the output; the bf16 path also rounds the filter taps to bf16
+    assert rel_err(pool.cpu().sum(1), ref.sum((2, 3))) <= tol(prec, 1e-5, 3e-3)
 
 
 @pytest.mark.parametrize("prec", PRECS)
