@@ -119,14 +119,14 @@ def cpu_oracle_videos_per_sec(batch: int, frames: int, identities, steps: int, w
     return batch / sec, sec, cores
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     b = args.cpu_batch
     v, sec, cores = cpu_oracle_videos_per_sec(b, args.frames, args.identities, args.steps, args.warmup)
     sample = f"{b} clips x {args.frames} frames per step (bounded sample of the batch={args.batch} workload)"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -164,8 +164,19 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
+    # stdout carries exactly ONE JSON line: anything libraries print on fd 1 while we run (e.g. NCCL's
+    # version banner) is routed to stderr, the real stdout is restored just before the JSON is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import mintime_b200
@@ -224,9 +235,10 @@ def main():
             torch.cuda.current_stream().synchronize()                    # the caller reads the logits
         return logits_host
 
+    from mintime_b200 import dist as mdist
+
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        mdist.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
@@ -241,11 +253,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         barrier()
-        if dist is not None:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return mdist.max_over_ranks(ms, device=dev)     # device time, max over ranks
 
     lib = _lib.load()
     sampler = ClockSampler(local_rank)
@@ -327,7 +335,7 @@ def main():
         "kernels": kernels,
         "sum_kernel_ms_per_step": total_ms / prof_steps,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":

@@ -278,56 +278,73 @@ __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, c
 // One block handles kSeImgs images so the two small weight matrices are streamed from L2 once per
 // kSeImgs images; `we_t` is the expand weight transposed to [SQ][C] (lanes read consecutive channels).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kSeImgs = 4;
+// One block per image.  The work is tiny (2*SQ*C MACs); what matters is memory-level parallelism on the
+// weight reads from L2: each warp owns a slice of the channels and walks all SQ rows with independent,
+// coalesced loads (phase 2), each thread owns channels and walks all SQ rows (phase 3).
 __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int n_chunks, float inv_hw,
                                                       const float* __restrict__ wr, const float* __restrict__ br,
                                                       const float* __restrict__ we_t, const float* __restrict__ be,
                                                       float* __restrict__ gate, int n_img, int C, int SQ) {
   extern __shared__ float sm[];
-  float* mean = sm;                  // [kSeImgs][C]
-  float* sq = sm + kSeImgs * C;      // [kSeImgs][SQ]
-  const int img0 = blockIdx.x * kSeImgs;
-  const int imgs = min(kSeImgs, n_img - img0);
-  for (int e = threadIdx.x; e < imgs * C; e += blockDim.x) {
-    const int i = e / C, c = e - i * C;
+  float* mean = sm;                  // [C]
+  float* sq = sm + C;                // [SQ]
+  float* part = sq + SQ;             // [8][SQ]
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < C; c += 256) {
     double acc = 0.0;                // fixed order, double: deterministic and as accurate as the reference's mean
-    for (int j = 0; j < n_chunks; ++j) acc += (double)pool_part[((size_t)(img0 + i) * n_chunks + j) * C + c];
-    mean[i * C + c] = (float)(acc * (double)inv_hw);
+    for (int j = 0; j < n_chunks; ++j) acc += (double)pool_part[((size_t)img * n_chunks + j) * C + c];
+    mean[c] = (float)(acc * (double)inv_hw);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < SQ; j += nwarps) {
-    float s[kSeImgs];
-#pragma unroll
-    for (int i = 0; i < kSeImgs; ++i) s[i] = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float wv = wr[(size_t)j * C + c];
-#pragma unroll
-      for (int i = 0; i < kSeImgs; ++i)
-        if (i < imgs) s[i] = fmaf(wv, mean[i * C + c], s[i]);
+  // phase 2: s[j] = swish(br[j] + sum_c wr[j][c] * mean[c]); warp w covers channels [c_lo, c_hi)
+  const int per_warp = ((C + 7) / 8 + 31) / 32 * 32;
+  const int c_lo = warp * per_warp, c_hi = min(C, c_lo + per_warp);
+  for (int j0 = 0; j0 < SQ; j0 += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int c = c_lo + lane; c < c_hi; c += 32) {
+      const float m = mean[c];
+      const float* wp = wr + (size_t)j0 * C + c;
+      a0 = fmaf(wp[0], m, a0);
+      if (j0 + 1 < SQ) a1 = fmaf(wp[C], m, a1);
+      if (j0 + 2 < SQ) a2 = fmaf(wp[2 * (size_t)C], m, a2);
+      if (j0 + 3 < SQ) a3 = fmaf(wp[3 * (size_t)C], m, a3);
     }
 #pragma unroll
-    for (int i = 0; i < kSeImgs; ++i) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-      if (lane == 0 && i < imgs) sq[i * SQ + j] = silu<true>(s[i] + br[j]);
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (lane == 0) {
+      part[warp * SQ + j0] = a0;
+      if (j0 + 1 < SQ) part[warp * SQ + j0 + 1] = a1;
+      if (j0 + 2 < SQ) part[warp * SQ + j0 + 2] = a2;
+      if (j0 + 3 < SQ) part[warp * SQ + j0 + 3] = a3;
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s[kSeImgs];
-    const float bias = be[c];
+  if (tid < SQ) {
+    float s = br[tid];
 #pragma unroll
-    for (int i = 0; i < kSeImgs; ++i) s[i] = bias;
-    for (int j = 0; j < SQ; ++j) {
-      const float wv = we_t[(size_t)j * C + c];
-#pragma unroll
-      for (int i = 0; i < kSeImgs; ++i)
-        if (i < imgs) s[i] = fmaf(wv, sq[i * SQ + j], s[i]);
+    for (int w = 0; w < 8; ++w) s += part[w * SQ + tid];
+    sq[tid] = silu<true>(s);
+  }
+  __syncthreads();
+  // phase 3: gate[c] = sigmoid(be[c] + sum_j we_t[j][c] * s[j])
+  for (int c = tid; c < C; c += 256) {
+    float s0 = be[c], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int j = 0;
+    for (; j + 4 <= SQ; j += 4) {
+      const float* wp = we_t + (size_t)j * C + c;
+      s0 = fmaf(wp[0], sq[j], s0);
+      s1 = fmaf(wp[C], sq[j + 1], s1);
+      s2 = fmaf(wp[2 * (size_t)C], sq[j + 2], s2);
+      s3 = fmaf(wp[3 * (size_t)C], sq[j + 3], s3);
     }
-#pragma unroll
-    for (int i = 0; i < kSeImgs; ++i)
-      if (i < imgs) gate[(size_t)(img0 + i) * C + c] = sigmoidf_<true>(s[i]);
+    for (; j < SQ; ++j) s0 = fmaf(we_t[(size_t)j * C + c], sq[j], s0);
+    gate[(size_t)img * C + c] = sigmoidf_<true>((s0 + s1) + (s2 + s3));
   }
 }
 
@@ -381,15 +398,15 @@ int launch_dw_tc_ks(const CUtensorMap& tm, const float* w, const float* shift, b
                     int W, int C, const DwTcGeom& g, const SeArgs& se, cudaStream_t st) {
   const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
   auto kern = dwconv_tc_kernel<K, S>;
-  const size_t smem = (size_t)std::max(g.tile_bytes, (C + se.sq) * 4) + 1024;
+  const size_t smem = 2 * (size_t)((g.tile_bytes + 1023) & ~1023) + (size_t)(C + se.sq) * 4 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(dwconv_tc)");
     attr_set = true;
   }
-  dim3 grid(g.tiles_x * g.tiles_y, g.n_cchunks, n_img);
-  kern<<<grid, 256, smem, st>>>(tm, w, shift, o, pool, Ho, Wo, C, same_pad_lo(H, K, S), g, se);
+  dim3 grid(g.workers, g.n_cchunks);      // persistent: each block walks images blockIdx.x, +workers, ...
+  kern<<<grid, 256, smem, st>>>(tm, w, shift, o, pool, n_img, Ho, Wo, C, same_pad_lo(H, K, S), g, se);
   MT_LAUNCH_CHECK("dwconv_tc_kernel");
   return MT_OK;
 }
@@ -401,8 +418,11 @@ int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, 
     return MT_ERR_UNSUPPORTED;
   }
   const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
-  const DwTcGeom g = dw_tc_geom(H, W, C, k, s);
-  MT_REQUIRE(g.IW <= 256 && g.IH <= 256 && g.tile_bytes <= 62 * 1024, "dwconv: tile too large (%dx%d)", g.IW, g.IH);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const DwTcGeom g = dw_tc_geom(H, W, C, k, s, n_img, sms > 0 ? sms : 148);
+  MT_REQUIRE(g.IW <= 256 && g.IH <= 256 && g.tile_bytes <= 56 * 1024, "dwconv: tile too large (%dx%d)", g.IW, g.IH);
   CUtensorMap tm;
   int rc = make_tmap_nhwc_bf16(&tm, in, n_img, H, W, C, g.IW, g.IH);
   if (rc) return rc;
@@ -418,10 +438,7 @@ int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, 
 }
 
 int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
-  if (precision == MT_PREC_BF16) {
-    const DwTcGeom g = dw_tc_geom(h, w_, c, k, s);
-    return g.tiles_x * g.tiles_y;
-  }
+  if (precision == MT_PREC_BF16) return 1;   // tensor-core kernel: a block sees every tile of an image -> one sum
   return dw_geom(h, w_, c, k, s).chunks;
 }
 
@@ -527,13 +544,12 @@ extern "C" int mt_dwconv_se_fwd(int precision, const void* in, const float* w, c
 extern "C" int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br,
                               const float* we, const float* be, float* gate, int n_img, int c, int sq, void* stream) {
   MT_REQUIRE(pool_part && wr && br && we && be && gate, "se_gate: null pointer");
-  MT_REQUIRE(n_img > 0 && c > 0 && sq > 0 && hw > 0 && n_chunks > 0 && (size_t)(c + sq) * 4 * kSeImgs <= 48 * 1024,
+  MT_REQUIRE(n_img > 0 && c > 0 && sq > 0 && sq <= 256 && hw > 0 && n_chunks > 0 && (size_t)(c + 9 * sq) * 4 <= 48 * 1024,
              "se_gate: bad shape");
   ProfScope prof(reinterpret_cast<cudaStream_t>(stream), 4.0 * n_img * (double)c * sq,
                  (double)n_img * c * 4 * (n_chunks + 1), "se_gate");
-  se_gate_kernel<<<(n_img + kSeImgs - 1) / kSeImgs, 256, (size_t)(c + sq) * 4 * kSeImgs,
-                   reinterpret_cast<cudaStream_t>(stream)>>>(pool_part, n_chunks, 1.0f / (float)hw, wr, br, we, be, gate,
-                                                             n_img, c, sq);
+  se_gate_kernel<<<n_img, 256, (size_t)(c + 9 * sq) * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
+      pool_part, n_chunks, 1.0f / (float)hw, wr, br, we, be, gate, n_img, c, sq);
   MT_LAUNCH_CHECK("se_gate_kernel");
   return MT_OK;
 }
@@ -594,12 +610,14 @@ extern "C" int mt_mbconv_fwd(int precision, const mt_mbconv_spec_t* spec, const 
     if (rc) return rc;
     dw_in = bexp;
   }
-  int* counters = reinterpret_cast<int*>(ws + l.counters);
-  cudaError_t ce = cudaMemsetAsync(counters, 0, (size_t)n_img * sizeof(int), reinterpret_cast<cudaStream_t>(stream));
-  if (ce != cudaSuccess) return cuda_status(ce, "cudaMemsetAsync(se counters)");
-  rc = mt_dwconv_se_fwd(precision, dw_in, w->dw_w, w->dw_shift, bdw, pool, counters, w->se_reduce_w, w->se_reduce_b,
-                        w->se_expand_w, w->se_expand_b, gate, n_img, b.hw_in, b.hw_in, cexp, b.kernel, b.stride, sq,
-                        stream);
+  // depthwise (+ pool sums) and the SE excitation as two launches: the gate needs the whole image's pool, and
+  // one block per image with all 512 images in flight hides the FC latency far better than a fused tail
+  // (mt_dwconv_se_fwd keeps the fused variant; it serialises ~30 us of FC latency per image inside blocks)
+  rc = mt_dwconv_fwd(precision, dw_in, w->dw_w, w->dw_shift, bdw, pool, n_img, b.hw_in, b.hw_in, cexp, b.kernel,
+                     b.stride, stream);
+  if (rc) return rc;
+  rc = mt_se_gate_fwd(pool, dw_chunks(precision, b.hw_in, b.hw_in, cexp, b.kernel, b.stride), ho * ho, w->se_reduce_w,
+                      w->se_reduce_b, w->se_expand_w, w->se_expand_b, gate, n_img, cexp, sq, stream);
   if (rc) return rc;
   const bool skip = b.stride == 1 && b.cin == b.cout;   // model.py:123
   return mt_pointwise_fwd(precision, bdw, w->project.w, w->project.shift, gate, ho * ho, skip ? in : nullptr, 0, out,

@@ -1,0 +1,76 @@
+"""CPU, world_size 2, gloo: the rank-to-rank plumbing of the replicas-only multi-GPU path."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, q):
+    sys.path.insert(0, ROOT)
+    import mintime_b200  # noqa: F401
+    from mintime_b200 import dist as mdist
+    from mintime_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = mdist.shard_range(total, rank, world)
+    # each rank "computes" logits for its shard of the seeded batch (the value encodes the global clip index)
+    meta = synth.make_batch_meta(total, 8, [1, 2], seed=5)
+    local = torch.arange(a, b, dtype=torch.float32).unsqueeze(1) + meta["mask"][a:b].float().sum(1, keepdim=True) * 100
+    full = mdist.gather_rows(local, total)
+    ms = mdist.max_over_ranks(10.0 + rank)
+    mdist.barrier()
+    q.put((rank, a, b, full.flatten().tolist(), ms))
+    dist.destroy_process_group()
+
+
+def test_shard_gather_and_max_over_ranks():
+    world, total = 2, 7            # ragged: 4 + 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, ROOT)
+    import mintime_b200  # noqa: F401
+    from mintime_b200 import synth
+    meta = synth.make_batch_meta(total, 8, [1, 2], seed=5)
+    expect = (torch.arange(total, dtype=torch.float32) + meta["mask"].float().sum(1) * 100).tolist()
+    assert [(r[1], r[2]) for r in res] == [(0, 4), (4, 7)]
+    for r in res:
+        assert r[3] == expect               # every rank sees the whole batch, in clip order
+        assert r[4] == 11.0                 # max over ranks
+
+
+def test_shard_range_properties():
+    sys.path.insert(0, ROOT)
+    import mintime_b200  # noqa: F401
+    from mintime_b200.dist import shard_range
+    for total in (0, 1, 5, 32, 64, 100):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
