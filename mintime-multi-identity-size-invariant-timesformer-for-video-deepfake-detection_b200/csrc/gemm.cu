@@ -15,6 +15,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -559,8 +562,23 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   return MT_OK;
 }
 
+#include "gemm2.cuh"
+
+bool tc2_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MINTIME_B200_NO_TC2");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 template <int KIND, bool GATED>
 int launch_tc(const GemmArgs& g, cudaStream_t stream) {
+  if constexpr (!GATED && (KIND == EPI_STORE || KIND == EPI_GEGLU || KIND == EPI_RESID_F32)) {
+    // large transformer contractions: CTA-pair kernel (256x256 tiles, cta_group::2)
+    if (tc2_enabled() && tc2_eligible(g)) return launch_tc2<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
+  }
   // per-row gathers (skip connection, embedding rows) use the direct epilogue; everything else TMA
   if (KIND == EPI_PATCH_EMBED || (KIND == EPI_STORE && g.epi.resid)) return launch_tc_impl<KIND, GATED, false>(g, stream);
   if ((g.epi.ldo * (KIND == EPI_RESID_F32 ? 4 : 2)) % 16 != 0 || (reinterpret_cast<uintptr_t>(g.epi.out) & 15))

@@ -1,0 +1,298 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 GEMM for the large transformer contractions.
+// Included by gemm.cu inside its anonymous namespace (uses PipeState, staging_piece, fast_gelu, ...).
+//
+// Why: with one CTA per 128x256 tile every k-block pulls 48 KiB of operands from L2 per 512 MMA cycles
+// (94 B/clk/SM), but an SM can only pull ~42 B/clk from L2 -- the round-1 kernels sat at 45-50 % tensor-pipe
+// for exactly that reason (QKV 43 us, FF2 61 us match bytes / 42 B/clk).  A CTA pair computes a 256x256 tile:
+// each CTA loads its own 128 rows of A and HALF of the W tile (128 rows), the pair's MMA reads both halves,
+// so per-SM operand traffic drops to 32 KiB per k-block (1.5x less) and 6 pipeline stages fit.
+//
+//   warp 0      TMA producer (both CTAs; bytes are credited to the leader CTA's full barrier)
+//   warp 1      MMA issuer (leader CTA only): tcgen05.mma.cta_group::2, M = 256, N = 256; accumulator rows
+//               0-127 live in the leader's TMEM, rows 128-255 in the peer's; double buffered (2 x 256 cols)
+//   warps 2..   epilogue (4 or 8 warps per CTA): own TMEM rows -> bias / swish / GEGLU / fp32 reduce-add ->
+//               swizzled staging -> TMA store; 8 warps (two groups alternating 128-byte column chunks) for
+//               the math-heavy GEGLU epilogue
+#pragma once
+
+constexpr int kStage2Bytes = 2 * kAStageBytes;   // A 128x64 + this CTA's half of W (128x64)
+// pipeline depth: 6 x 32 KiB + one epilogue group's staging (32 KiB), or 5 x 32 KiB + two groups' (64 KiB)
+constexpr int stages2(int epi_warps) { return epi_warps == 8 ? 5 : 6; }
+
+struct Tc2Params {
+  int M, N, K;
+  int tiles_m, tiles_n;    // 256 x 256 pair tiles
+  EpiParams epi;
+};
+
+template <int KIND, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_out, Tc2Params p) {
+  constexpr int kGroups = EPI_WARPS / 4;           // epilogue warp groups (each owns 2 staging buffers)
+  constexpr int kStages2 = stages2(EPI_WARPS);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages2 * kAStageBytes;
+  uint8_t* smem_stage = smem_b + kStages2 * kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + kGroups * 2 * kStagingBytes);
+  uint64_t* full_bar = bars;                       // used in the leader CTA
+  uint64_t* empty_bar = bars + kStages2;           // both CTAs (multicast commit)
+  uint64_t* tmem_full = bars + 2 * kStages2;       // both CTAs (multicast commit)
+  uint64_t* tmem_empty = tmem_full + 2;            // used in the leader CTA (both epilogues arrive)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();    // 0 = leader
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    ptx::prefetch_tmap(&tmap_out);
+    for (int s = 0; s < kStages2; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 2 * EPI_WARPS * 32);
+    }
+    ptx::fence_mbar_init();
+  }
+  ptx::cluster_sync_all();                         // barriers of both CTAs initialised before any remote use
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_ptr_smem, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      PipeState ps;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128;
+        const int n0 = (tile % p.tiles_n) * 256 + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[ps.stage], 2u * kStage2Bytes);   // both CTAs' bytes
+          ptx::tma_load_2d_2sm(smem_a + ps.stage * kAStageBytes, &tmap_a, &full_bar[ps.stage], kb * kBlockK, m0);
+          ptx::tma_load_2d_2sm(smem_b + ps.stage * kAStageBytes, &tmap_b, &full_bar[ps.stage], kb * kBlockK, n0);
+          ps.advance(kStages2);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA)
+    if (leader && lane == 0) {
+      PipeState ps;
+      const uint32_t idesc = ptx::umma_idesc_bf16_f32(256, 256);
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem_a + ps.stage * kAStageBytes);
+          const uint32_t b_addr = ptx::smem_u32(smem_b + ps.stage * kAStageBytes);
+          const int k_left = p.K - kb * kBlockK;
+          const int ksteps = k_left >= kBlockK ? 4 : (k_left + 15) / 16;
+          for (int k = 0; k < ksteps; ++k)
+            ptx::umma_bf16_ss_2sm(tmem_d, ptx::umma_smem_desc_sw128(a_addr + k * 32),
+                                  ptx::umma_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit_2sm(&empty_bar[ps.stage], 0x3);   // frees the stage in BOTH CTAs
+          ps.advance(kStages2);
+        }
+        ptx::umma_commit_2sm(&tmem_full[as], 0x3);            // accumulator ready in BOTH CTAs
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (EPI_WARPS warps)
+    const int ew = warp - 2;
+    const int grp = ew >> 2;                       // warp group: alternates 128-byte column chunks
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int trow = quad * 32 + lane;
+    const bool issuer = (ew & 3) == 0 && lane == 0;
+    const EpiParams& e = p.epi;
+    uint8_t* my_stage = smem_stage + grp * 2 * kStagingBytes;
+    uint32_t store_it = 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128;
+      const int n0 = (tile % p.tiles_n) * 256;
+      ptx::mbar_wait(&tmem_full[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
+      constexpr int kChunk = KIND == EPI_GEGLU ? 128 : (KIND == EPI_RESID_F32 ? 32 : 64);
+      constexpr int kChunks = 256 / kChunk;
+      for (int ci = grp; ci < kChunks; ci += kGroups) {
+        const int c = ci * kChunk;
+        uint8_t* stg = my_stage + (store_it & 1) * kStagingBytes;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (KIND == EPI_GEGLU) {
+#pragma unroll
+          for (int ob = 0; ob < 2; ++ob) {
+            uint32_t ru[32], rg[32];
+            ptx::tmem_ld_32x32b_x32(taddr + c + ob * 64, ru);
+            ptx::tmem_ld_32x32b_x32(taddr + c + ob * 64 + 32, rg);
+            ptx::tmem_ld_wait();
+            const int col = n0 + c + ob * 64;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float u[8], gg[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { u[i] = __uint_as_float(ru[g * 8 + i]); gg[i] = __uint_as_float(rg[g * 8 + i]); }
+              if (e.bias) {
+                float b[8];
+                load8(e.bias + col + g * 8, b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[i] += b[i];
+                load8(e.bias + col + 32 + g * 8, b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gg[i] += b[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] *= fast_gelu(gg[i]);
+              *staging_piece(stg, trow, ob * 4 + g) =
+                  make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
+            }
+          }
+        } else {
+          constexpr int kQ = kChunk / 16;
+          uint32_t r[kQ][16];
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) ptx::tmem_ld_32x32b_x16(taddr + c + q * 16, r[q]);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int col = n0 + c + q * 16 + hh * 8;
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q][hh * 8 + i]);
+              if (e.bias) {
+                float b[8];
+                load8(e.bias + col, b);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += b[i];
+              }
+              if (KIND == EPI_STORE) {
+                if (e.act == 1) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = silu<false>(v[i]);
+                }
+                *staging_piece(stg, trow, q * 2 + hh) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              } else {
+                *staging_piece(stg, trow, q * 4 + hh * 2) =
+                    make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                *staging_piece(stg, trow, q * 4 + hh * 2 + 1) =
+                    make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+              }
+            }
+          }
+        }
+        if (ci + kGroups >= kChunks) {             // this group's last TMEM read of the tile
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_cluster(&tmem_empty[as], 0);   // the leader's MMA warp waits for both CTAs
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (issuer) {
+          const int ocol = KIND == EPI_GEGLU ? (n0 + c) / 2 : n0 + c;
+          if (KIND == EPI_RESID_F32)
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(ptx::smem_u32(stg)), "r"(ocol), "r"(m0)
+                         : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(ptx::smem_u32(stg)), "r"(ocol), "r"(m0)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++store_it;
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                         // nobody may still target this CTA's smem / TMEM
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <int KIND, int EPI_WARPS>
+int launch_tc2(const GemmArgs& g, cudaStream_t stream) {
+  Tc2Params p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.epi = g.epi;
+  p.tiles_m = (g.M + 255) / 256;
+  p.tiles_n = g.N / 256;
+  constexpr int kGroups = EPI_WARPS / 4;
+  constexpr int kStages2 = stages2(EPI_WARPS);
+  const size_t smem = (size_t)kStages2 * kStage2Bytes + (size_t)kGroups * 2 * kStagingBytes + 1024 +
+                      (2 * kStages2 + 4) * 8 + 16;
+  CUtensorMap ta, tb, tout;
+  int rc = make_tmap_2d(&ta, g.a, false, g.M, g.K, g.K, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tb, g.w, false, g.N, g.K, g.K, 128);
+  if (rc) return rc;
+  const bool f32 = KIND == EPI_RESID_F32;
+  rc = make_tmap_2d(&tout, g.epi.out, f32, g.M, KIND == EPI_GEGLU ? g.N / 2 : g.N, g.epi.ldo, 128);
+  if (rc) return rc;
+  auto kern = gemm_tc2_kernel<KIND, EPI_WARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc2)");
+    attr_set = true;
+  }
+  int pairs = std::min(p.tiles_m * p.tiles_n, num_sms() / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(64 + 32 * EPI_WARPS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, p);
+  if (e != cudaSuccess) return cuda_status(e, "cudaLaunchKernelEx(gemm_tc2)");
+  MT_LAUNCH_CHECK("gemm_tc2_kernel");
+  return MT_OK;
+}
+
+// eligibility: plain store / GEGLU / fp32 residual epilogues, N a multiple of the 256-wide pair tile,
+// enough rows to fill the chip, 16-byte aligned output rows
+inline bool tc2_eligible(const GemmArgs& g) {
+  if (g.gate || g.epi.resid) return false;
+  if (g.epi.kind != EPI_STORE && g.epi.kind != EPI_GEGLU && g.epi.kind != EPI_RESID_F32) return false;
+  if (g.N % 256 != 0 || g.M < 4096 || g.K < 64) return false;
+  if ((g.epi.ldo * (g.epi.kind == EPI_RESID_F32 ? 4 : 2)) % 16 != 0 || (reinterpret_cast<uintptr_t>(g.epi.out) & 15)) return false;
+  return true;
+}

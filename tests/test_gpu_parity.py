@@ -57,6 +57,8 @@ def tol(p, fp32=2e-5, bf16=1e-2):
     (98, 1280, 320, 1, False),      # head conv
     (5000, 672, 112, 1, False),     # 3 x 224-wide tiles
     (40000, 16, 32, 0, False),      # block-0 project: narrowest tile, many row tiles (persistent loop)
+    (4500, 512, 320, 1, False),     # CTA-pair (cta_group::2) kernel: 256x256 tiles, ragged M, K tail-free
+    (25120, 1536, 512, 0, False),   # to_qkv at the bench size (CTA-pair kernel, 99 x 6 tiles over 74 pairs)
 ])
 def test_pointwise(prec, m, n, k, act, res):
     a = rnd((m, k), 1).to(T(prec)); w = rnd((n, k), 2, k ** -0.5).to(T(prec))
@@ -85,7 +87,7 @@ def test_pointwise_with_se_gate(prec, imgs, hw, n, k):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("m,n,k", [(785 * 2, 512, 512), (1000, 512, 2048)])
+@pytest.mark.parametrize("m,n,k", [(785 * 2, 512, 512), (1000, 512, 2048), (5000, 512, 512), (25120, 512, 2048)])
 def test_linear_residual(prec, m, n, k):
     a = rnd((m, k), 1).to(T(prec)); w = rnd((n, k), 2, k ** -0.5).to(T(prec)); b = rnd((n,), 3); x = rnd((m, n), 4)
     ref = x + a.float() @ w.float().t() + b
@@ -96,7 +98,7 @@ def test_linear_residual(prec, m, n, k):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("m,n,k", [(500, 4096, 512), (130, 256, 64)])
+@pytest.mark.parametrize("m,n,k", [(500, 4096, 512), (130, 256, 64), (4200, 1024, 512), (25120, 4096, 512)])
 def test_linear_geglu(prec, m, n, k):
     a = rnd((m, k), 1).to(T(prec)); w = rnd((n, k), 2, k ** -0.5).to(T(prec)); b = rnd((n,), 3, 0.2)
     h = a.float() @ w.float().t() + b

@@ -40,8 +40,8 @@ def test_argument_validation_without_gpu():
     rc = lib.mt_divided_attn_fwd(1, 8, 8, 8, 0, 8, None, 1, 16, 49, 8, 32, None)     # dim_head != 64
     assert rc == -1 and b"dim_head" in lib.mt_last_error()
     assert lib.mt_effnet_b0_workspace_bytes(0, 1) == 0
-    assert lib.mt_effnet_b0_workspace_bytes(4, 1) * 2 > lib.mt_effnet_b0_workspace_bytes(4, 0) > \
-        lib.mt_effnet_b0_workspace_bytes(4, 1) > 0
+    bf16_ws, fp32_ws = lib.mt_effnet_b0_workspace_bytes(4, 1), lib.mt_effnet_b0_workspace_bytes(4, 0)
+    assert 0 < bf16_ws < fp32_ws <= 2.1 * bf16_ws          # fp32 activations are twice as wide
 
 
 def test_effnet_state_dict_matches_reference_names():
