@@ -201,6 +201,12 @@ int mt_mbconv_fwd(int precision, const mt_mbconv_spec_t* spec, const mt_mbconv_t
 int mt_head_fwd(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* bias, float* logits,
                 int batch, int tokens, int dim, int num_classes, void* stream);
 
+/* Attention aggregation of predict.py/test.py (utils.py:68-96), per video: per-token max over heads of the CLS
+ * attention maps, np.array_split into num_frames chunks, mean * scale, softmax over frames; for the space map,
+ * the time map and their sum.  space_attn/time_attn f32 [batch*heads][tokens] -> out f32 [batch][3][num_frames]. */
+int mt_aggregate_attn_fwd(const float* space_attn, const float* time_attn, float* out, int batch, int heads,
+                          int num_frames, int tokens, float scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Diagnostics (used by bench.py; off by default, no effect on results)
  * ------------------------------------------------------------------------------------------- */

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) attn_cls_kernel(const T* __restrict__ qkv
   float* sc = sm;              // [N]
   float* q0 = sm + N;          // [64]
   float* red = q0 + 64;        // [32]
-  float* part = red + 32;      // [4][64]
+  float* part = red + 32;      // [32][64] partial outputs
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int inner = heads * 64, ld = 3 * inner;
   const T* base = qkv + (size_t)b * N * ld;
@@ -133,13 +133,28 @@ __global__ void __launch_bounds__(256) attn_cls_kernel(const T* __restrict__ qkv
     if (cls_attn) cls_attn[(size_t)blockIdx.x * N + j] = pj;
   }
   __syncthreads();
-  const int d = tid & 63, pr = tid >> 6;
-  float o = 0.f;
-  for (int j = pr; j < N; j += 4) o = fmaf(sc[j], to_f(base[(size_t)j * ld + 2 * inner + h * 64 + d]), o);
-  part[pr * 64 + d] = o;
+  // o = P V: thread = (key group kg of 32, 8-dim chunk dc); 16-byte (8-dim) loads of the V rows, ~25
+  // independent loads per thread, then a fixed-order reduction over the 32 key groups in shared memory
+  const int dc = tid & 7, kg = tid >> 3;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int j = kg; j < N; j += 32) {
+    float vv[8];
+    load8(base + (size_t)j * ld + 2 * inner + h * 64 + dc * 8, vv);
+    const float pj = sc[j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vv[i], acc[i]);
+  }
+  __syncthreads();
+  float* partial = part;                 // [32][64] floats
+#pragma unroll
+  for (int i = 0; i < 8; ++i) partial[kg * 64 + dc * 8 + i] = acc[i];
   __syncthreads();
   if (tid < 64) {
-    const float r = (part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]);
+    float r = 0.f;
+#pragma unroll 8
+    for (int g = 0; g < 32; ++g) r += partial[g * 64 + tid];
     out[(size_t)b * N * inner + h * 64 + tid] = from_f<T>(r);
   }
 }
@@ -276,7 +291,7 @@ int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, i
   const int N = 1 + f * n;
   const T* q = reinterpret_cast<const T*>(qkv);
   T* o = reinterpret_cast<T*>(out);
-  const size_t smem = (size_t)(N + 64 + 32 + 256) * sizeof(float);
+  const size_t smem = (size_t)(N + 64 + 32 + 2048) * sizeof(float);
   {
     ProfScope prof(st, 4.0 * B * heads * 64.0 * N, (double)B * N * heads * 64 * 2 * sizeof(T), "attn_cls");
     attn_cls_kernel<T><<<B * heads, 256, smem, st>>>(q, mask, o, cls_attn, N, f, n, heads);
@@ -379,7 +394,7 @@ extern "C" int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t
   MT_REQUIRE(dim_head == 64, "divided_attn: dim_head must be 64 (got %d)", dim_head);
   MT_REQUIRE(batch > 0 && heads > 0 && f >= 1 && f <= 63 && n >= 1 && n <= 63, "divided_attn: bad shape B=%d f=%d n=%d",
              batch, f, n);
-  MT_REQUIRE((size_t)(1 + f * n + 352) * 4 <= 48 * 1024, "divided_attn: too many tokens (%d)", 1 + f * n);
+  MT_REQUIRE((size_t)(1 + f * n + 2144) * 4 <= 48 * 1024, "divided_attn: too many tokens (%d)", 1 + f * n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (precision == MT_PREC_FP32)
     return launch_attn_t<float>(qkv, mask, identities_mask, mode, out, cls_attn, batch, f, n, heads, st);
@@ -491,4 +506,60 @@ extern "C" int mt_tsf_fwd(const mt_tsf_weights_t* w, const mt_tsf_cfg_t* cfg, co
     if (rc) return rc;
   }
   return mt_head_fwd(x, w->out_ln_g, w->out_ln_b, w->out_w, w->out_b, logits, batch, N, D, cfg->num_classes, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Attention aggregation of predict.py / test.py (reference utils.py:68-96), per video on the device:
+//   tok[i]  = max over heads of the CLS attention of token i            (utils.py:75, written for b = 1)
+//   chunks  = np.array_split(tok, f): the first N % f chunks hold N/f + 1 tokens (chunk 0 = CLS + frame 0)
+//   out[k]  = softmax_k( mean(chunk_k) * scale )                         (utils.py:84-86)
+// for space, time and their elementwise sum -> out [B][3][f].  One block per video.
+// ---------------------------------------------------------------------------------------------------
+namespace mt {
+namespace {
+__global__ void __launch_bounds__(256) aggregate_attn_kernel(const float* __restrict__ space, const float* __restrict__ time,
+                                                             float* __restrict__ out, int heads, int f, int N, float scale) {
+  extern __shared__ float sm[];
+  float* tok = sm;              // [3][N]
+  float* fm = sm + 3 * N;       // [3][f]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < N; i += 256) {
+    float ms = -FLT_MAX, mt_ = -FLT_MAX;
+    for (int h = 0; h < heads; ++h) {
+      ms = fmaxf(ms, space[((size_t)b * heads + h) * N + i]);
+      mt_ = fmaxf(mt_, time[((size_t)b * heads + h) * N + i]);
+    }
+    tok[i] = ms; tok[N + i] = mt_; tok[2 * N + i] = ms + mt_;
+  }
+  __syncthreads();
+  const int base = N / f, rem = N % f;
+  for (int e = tid; e < 3 * f; e += 256) {
+    const int which = e / f, k = e % f;
+    const int start = k * base + min(k, rem), len = base + (k < rem ? 1 : 0);
+    float s = 0.f;
+    for (int i = 0; i < len; ++i) s += tok[which * N + start + i];
+    fm[e] = s / (float)len * scale;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    float mx = -FLT_MAX;
+    for (int k = 0; k < f; ++k) mx = fmaxf(mx, fm[tid * f + k]);
+    float den = 0.f;
+    for (int k = 0; k < f; ++k) den += expf(fm[tid * f + k] - mx);
+    for (int k = 0; k < f; ++k) out[((size_t)b * 3 + tid) * f + k] = expf(fm[tid * f + k] - mx) / den;
+  }
+}
+}  // namespace
+}  // namespace mt
+
+extern "C" int mt_aggregate_attn_fwd(const float* space_attn, const float* time_attn, float* out, int batch, int heads,
+                                     int num_frames, int tokens, float scale, void* stream) {
+  MT_REQUIRE(space_attn && time_attn && out && batch > 0 && heads > 0 && num_frames > 0 && tokens >= num_frames,
+             "aggregate_attn: bad argument");
+  const size_t smem = (size_t)(3 * tokens + 3 * num_frames) * sizeof(float);
+  MT_REQUIRE(smem <= 48 * 1024, "aggregate_attn: too many tokens (%d)", tokens);
+  mt::aggregate_attn_kernel<<<batch, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(space_attn, time_attn, out, heads,
+                                                                                         num_frames, tokens, scale);
+  MT_LAUNCH_CHECK("aggregate_attn_kernel");
+  return MT_OK;
 }

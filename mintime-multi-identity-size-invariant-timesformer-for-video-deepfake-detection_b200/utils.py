@@ -1,0 +1,54 @@
+"""Host-side mirror of the reference's ``utils.aggregate_attentions`` (utils.py:68-96), computed on
+the device by mt_aggregate_attn_fwd.  No CPU fallback."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def aggregate_attentions_batched(attentions: Sequence[torch.Tensor], heads: int, num_frames: int,
+                                 scale_factor: float = 50000.0) -> torch.Tensor:
+    """attentions = [space_attn, time_attn], each (B*heads, 1, N) float32 on the GPU (what
+    SizeInvariantTimeSformer returns with require_attention=True).  Returns (B, 3, num_frames):
+    per video the softmaxed per-frame attention for space, time and space+time.
+
+    The reference takes the max over batch AND heads (utils.py:75; it is only ever called with B = 1);
+    this version keeps videos separate, which is identical for B = 1."""
+    space, time = attentions
+    if space.dim() == 3:
+        space, time = space.squeeze(1), time.squeeze(1)
+    space = space.contiguous().float()
+    time = time.contiguous().float()
+    rows, n_tok = space.shape
+    if rows % heads:
+        raise ValueError(f"{rows} attention rows are not a multiple of heads={heads}")
+    b = rows // heads
+    _lib.require_device(space.device)
+    out = torch.empty((b, 3, num_frames), dtype=torch.float32, device=space.device)
+    with torch.cuda.device(space.device):
+        rc = _lib.load().mt_aggregate_attn_fwd(space.data_ptr(), time.data_ptr(), out.data_ptr(), b, heads, num_frames,
+                                               n_tok, float(scale_factor), _lib.stream_ptr())
+    _lib.check(rc, "mt_aggregate_attn_fwd")
+    return out
+
+
+def aggregate_attentions(attentions, heads, num_frames, frames_per_identity, scale_factor=50000) -> Tuple[List, List]:
+    """Same signature and return values as the reference (utils.py:68-96) for a single video:
+    ([space, time, combined] as lists of num_frames floats, identity_attentions)."""
+    agg = aggregate_attentions_batched(attentions, heads, num_frames, scale_factor)
+    if agg.shape[0] != 1:
+        raise ValueError("aggregate_attentions mirrors the reference's single-video call; use "
+                         "aggregate_attentions_batched for B > 1")
+    aggregated = [agg[0, i].cpu().numpy() for i in range(3)]
+    identity_attentions = []
+    for index, identity_frames in enumerate(frames_per_identity):      # utils.py:88-95, kept verbatim in meaning
+        if index == 0:
+            identity_attention = sum(aggregated[-1][:identity_frames - 1])
+        else:
+            previous_identity_frames = frames_per_identity[index - 1]
+            identity_attention = sum(aggregated[-1][previous_identity_frames - 1:identity_frames - 1])
+        identity_attentions.append(identity_attention)
+    return aggregated, identity_attentions

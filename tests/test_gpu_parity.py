@@ -179,6 +179,37 @@ def test_patch_embed_tokens(prec):
     assert rel_err(x.cpu(), ref) <= tol(prec, 1e-5, 1e-4)
 
 
+def _ref_aggregate(attentions, heads, num_frames, scale_factor=50000):
+    """reference utils.py:68-86 restated with numpy (single video)."""
+    agg = []
+    for a in attentions:
+        a = a.squeeze(1).reshape(-1, heads, a.shape[-1]).numpy()
+        agg.append([a[:, :, i].max() for i in range(a.shape[2])])
+    agg.append(list(np.sum(np.asarray(agg), axis=0)))
+    out = []
+    for lst in agg:
+        chunks = np.array_split(np.asarray(lst), num_frames)
+        v = np.array([c.mean() * scale_factor for c in chunks], dtype=np.float64)
+        e = np.exp(v - v.max())
+        out.append(e / e.sum())
+    return out
+
+
+@pytest.mark.parametrize("f", [8, 16])
+def test_aggregate_attentions(f):
+    from mintime_b200.utils import aggregate_attentions, aggregate_attentions_batched
+    heads, N, B = 8, 1 + f * 49, 3
+    g = np.random.default_rng(4)
+    maps = [torch.from_numpy(g.dirichlet(np.ones(N) * 50, B * heads).astype(np.float32)).unsqueeze(1) for _ in range(2)]
+    out = aggregate_attentions_batched([m.to(DEV) for m in maps], heads, f).cpu().numpy()
+    for b in range(B):
+        ref = _ref_aggregate([m[b * heads:(b + 1) * heads] for m in maps], heads, f)
+        for i in range(3):
+            np.testing.assert_allclose(out[b, i], ref[i], rtol=2e-4, atol=1e-6)
+    agg, ident = aggregate_attentions([m[:heads].to(DEV) for m in maps], heads, f, [f // 2, f])
+    assert len(agg) == 3 and len(agg[0]) == f and len(ident) == 2
+
+
 # ------------------------------------------------------------------------------------------ extractor pieces
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("u8", [False, True])
