@@ -3,9 +3,12 @@
 // The 1x1 convolutions run in gemm.cu; this file holds the stencil / reduction kernels
 // (stem 3x3, depthwise kxk + BN + swish + SE squeeze, SE excitation) and the layer schedule.
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "dwconv_tc.cuh"
+#include "dwconv_umma.cuh"
 
 namespace mt {
 namespace {
@@ -411,6 +414,48 @@ int launch_dw_tc_ks(const CUtensorMap& tm, const float* w, const float* shift, b
   return MT_OK;
 }
 
+// stride-1 depthwise layers on tcgen05 (dwconv_umma.cuh): correct but 2-4x SLOWER than the mma.sync kernel
+// (each M128xN16xK16 tcgen05.mma costs ~190 cycles: it reads full 128-byte operand rows), so it is opt-in:
+// MINTIME_B200_DW=umma
+int dw_umma_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("MINTIME_B200_DW");
+    mode = (e && !strcmp(e, "umma")) ? 1 : 0;
+  }
+  return mode;
+}
+
+int launch_dw_umma(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
+                   int C, int k, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  DwUmmaGeom g = dw_umma_geom(H, W, C, k, n_img, sms > 0 ? sms : 148);
+  if (const char* e = getenv("MINTIME_B200_DW_BO")) g.use_base_offset = atoi(e);
+  const size_t smem = 2 * (size_t)g.slot_bytes + g.b_bytes + 1024;
+  MT_REQUIRE(g.IW <= 256 && g.IH <= 256 && smem <= 220 * 1024, "dwconv(umma): tile too large (%dx%d)", g.IW, g.IH);
+  CUtensorMap tm;
+  int rc = make_tmap_nhwc_bf16(&tm, in, n_img, H, W, C, g.IW, g.IH);
+  if (rc) return rc;
+  ProfScope prof(st, 2.0 * k * k * (double)n_img * H * W * C, (double)n_img * C * 2.0 * H * W * 2, "dwconv_umma k%d s1 C%d H%d",
+                 k, C, H);
+  dim3 grid(g.workers, g.n_cchunks);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  const int pad = same_pad_lo(H, k, 1);
+  if (k == 3) {
+    static bool a3 = false;
+    if (!a3) { cudaFuncSetAttribute(dwconv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); a3 = true; }
+    dwconv_umma_kernel<3><<<grid, 192, smem, st>>>(tm, w, shift, o, pool, n_img, H, W, C, pad, g);
+  } else {
+    static bool a5 = false;
+    if (!a5) { cudaFuncSetAttribute(dwconv_umma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); a5 = true; }
+    dwconv_umma_kernel<5><<<grid, 192, smem, st>>>(tm, w, shift, o, pool, n_img, H, W, C, pad, g);
+  }
+  MT_LAUNCH_CHECK("dwconv_umma_kernel");
+  return MT_OK;
+}
+
 int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
                  int C, int k, int s, SeArgs se, cudaStream_t st) {
   if ((k != 3 && k != 5) || (s != 1 && s != 2)) {
@@ -449,7 +494,11 @@ int dwconv_dispatch(int precision, const void* in, const float* w, const float* 
              "dwconv: bad shape n=%d h=%d w=%d c=%d (c %% 8 == 0)", n_img, h, w_, c);
   MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
   if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
-  if (precision == MT_PREC_BF16) return launch_dw_tc(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+  if (precision == MT_PREC_BF16) {
+    if (s == 1 && h == w_ && (k == 3 || k == 5) && !se.wr && dw_umma_mode() == 1)
+      return launch_dw_umma(in, w, shift, out, pool_part, n_img, h, w_, c, k, st);
+    return launch_dw_tc(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+  }
   if (precision == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);  // debug: CUDA-core bf16
   set_error("dwconv: unknown precision %d", precision);
   return MT_ERR_ARG;

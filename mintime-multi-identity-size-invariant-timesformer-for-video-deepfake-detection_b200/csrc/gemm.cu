@@ -325,6 +325,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m0 + r;
       const float* grow = p.gate + (size_t)((row < p.M ? row : p.M - 1) / p.rows_per_gate) * p.K;
       for (int kb = 0; kb < num_kb; ++kb) {
+        // the gate values do not depend on the tile: fetch them BEFORE waiting for the TMA so their L2
+        // latency overlaps the load instead of sitting on the TMA -> gate -> MMA critical path
+        float4 gv[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int k = kb * kBlockK + c * 8;
+          if (k < p.K) {
+            gv[2 * c] = *reinterpret_cast<const float4*>(grow + k);
+            gv[2 * c + 1] = *reinterpret_cast<const float4*>(grow + k + 4);
+          }
+        }
         ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
         uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
 #pragma unroll
@@ -334,8 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
             uint4 u = *ptr;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-            const float4 g0 = *reinterpret_cast<const float4*>(grow + k);
-            const float4 g1 = *reinterpret_cast<const float4*>(grow + k + 4);
+            const float4 g0 = gv[2 * c], g1 = gv[2 * c + 1];
             float2 f;
             f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
             f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
