@@ -178,25 +178,35 @@ __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, c
     if (pid >= patches) break;
     const int oy0 = (pid / patches_x) * R, ox0 = (pid % patches_x) * SX;
     const int iy0 = oy0 * S - pad_lo, ix0 = ox0 * S - pad_lo;
-    float acc[R][SX][8];
+    // accumulators and the input row window as packed float2 pairs: Blackwell's FFMA2 (fma.rn.f32x2) issues
+    // two fp32 FMAs per instruction; inputs are converted bf16 -> fp32 ONCE when loaded (each vector then feeds
+    // up to K*R taps), which halves the instruction count of the lazy-conversion version
+    float2 acc[R][SX][4];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int j = 0; j < SX; ++j)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[r][j][i] = 0.f;
+        for (int q = 0; q < 4; ++q) acc[r][j][q] = make_float2(0.f, 0.f);
 
 #pragma unroll
     for (int ir = 0; ir < NROW; ++ir) {
       const int iy = iy0 + ir;
       if (iy < 0 || iy >= H) continue;          // zero padding rows contribute nothing
-      Raw8<T> row[NIN];
+      float2 row[NIN][4];
       const T* rp = in_img + (size_t)iy * W * C;
 #pragma unroll
       for (int jj = 0; jj < NIN; ++jj) {
         const int ix = ix0 + jj;
-        if (ix >= 0 && ix < W) row[jj].load(rp + (size_t)ix * C);
-        else row[jj].zero();
+        if (ix >= 0 && ix < W) {
+          float v[8];
+          load8(rp + (size_t)ix * C, v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) row[jj][q] = make_float2(v[2 * q], v[2 * q + 1]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) row[jj][q] = make_float2(0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -207,9 +217,11 @@ __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, c
           float wv[8];
           load8(w + (size_t)(ky * K + kx) * C + c0, wv);
 #pragma unroll
-          for (int j = 0; j < SX; ++j)
+          for (int q = 0; q < 4; ++q) {
+            const float2 w2 = make_float2(wv[2 * q], wv[2 * q + 1]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[r][j][i] = fmaf(row[j * S + kx].get(i), wv[i], acc[r][j][i]);
+            for (int j = 0; j < SX; ++j) acc[r][j][q] = __ffma2_rn(row[j * S + kx][q], w2, acc[r][j][q]);
+          }
         }
       }
     }
@@ -224,7 +236,7 @@ __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, c
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          v[i] = silu<kExact>(acc[r][j][i] + sh[i]);
+          v[i] = silu<kExact>(((i & 1) ? acc[r][j][i >> 1].y : acc[r][j][i >> 1].x) + sh[i]);
           psum[i] += v[i];
         }
         store8(out_img + ((size_t)oy * Wo + ox) * C, v);
@@ -421,7 +433,7 @@ int dw_umma_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("MINTIME_B200_DW");
-    mode = (e && !strcmp(e, "umma")) ? 1 : 0;
+    mode = (e && !strcmp(e, "umma")) ? 1 : ((e && !strcmp(e, "simt")) ? 2 : 0);
   }
   return mode;
 }
@@ -483,7 +495,8 @@ int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, 
 }
 
 int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
-  if (precision == MT_PREC_BF16) return 1;   // tensor-core kernel: a block sees every tile of an image -> one sum
+  // tensor-core kernels: a block sees every tile of an image -> one sum per (image, channel)
+  if (precision == MT_PREC_BF16 && dw_umma_mode() != 2) return 1;
   return dw_geom(h, w_, c, k, s).chunks;
 }
 
@@ -495,6 +508,7 @@ int dwconv_dispatch(int precision, const void* in, const float* w, const float* 
   MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
   if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
   if (precision == MT_PREC_BF16) {
+    if (dw_umma_mode() == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
     if (s == 1 && h == w_ && (k == 3 || k == 5) && !se.wr && dw_umma_mode() == 1)
       return launch_dw_umma(in, w, shift, out, pool_part, n_img, h, w_, c, k, st);
     return launch_dw_tc(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
