@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "dwconv_simt.cuh"
 #include "dwconv_tc.cuh"
 #include "dwconv_umma.cuh"
 
@@ -429,13 +430,78 @@ int launch_dw_tc_ks(const CUtensorMap& tm, const float* w, const float* shift, b
 // stride-1 depthwise layers on tcgen05 (dwconv_umma.cuh): correct but 2-4x SLOWER than the mma.sync kernel
 // (each M128xN16xK16 tcgen05.mma costs ~190 cycles: it reads full 128-byte operand rows), so it is opt-in:
 // MINTIME_B200_DW=umma
+// MINTIME_B200_DW selects the bf16 depthwise kernel: (default) smem-staged FFMA2 kernel of dwconv_simt.cuh;
+// "tc" = mma.sync block-diagonal kernel, "umma" = tcgen05 variant, "simt" = register-strip kernel on global loads
 int dw_umma_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("MINTIME_B200_DW");
-    mode = (e && !strcmp(e, "umma")) ? 1 : ((e && !strcmp(e, "simt")) ? 2 : 0);
+    mode = 3;
+    if (e && !strcmp(e, "tc")) mode = 0;
+    if (e && !strcmp(e, "umma")) mode = 1;
+    if (e && !strcmp(e, "simt")) mode = 2;
   }
   return mode;
+}
+
+int device_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+
+template <int K, int S>
+int launch_dw_simt_ks(const CUtensorMap& tm, const float* w, const float* shift, bf16* o, float* pool, int n_img, int H,
+                      int C, const DwSimtGeom& g, cudaStream_t st) {
+  const int Ho = (H + S - 1) / S;
+  using Kern = void (*)(const CUtensorMap, const float*, const float*, bf16*, float*, int, int, int, int, int, DwSimtGeom);
+  const int slot = g.CW == 32 ? 1 : (g.CW == 48 ? 2 : (g.CW == 64 ? 3 : 0));
+  static const Kern kerns[4] = {dwconv_simt_kernel<K, S, 0>, dwconv_simt_kernel<K, S, 32>, dwconv_simt_kernel<K, S, 48>,
+                                dwconv_simt_kernel<K, S, 64>};
+  Kern kern = kerns[slot];
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(dwconv_simt)");
+    attr_set[slot] = true;
+  }
+  // persistent blocks, statically scheduled: launch exactly as many as are co-resident (registers included),
+  // so no block waits for a second wave
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.threads, g.smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const long long work = (long long)n_img * g.tiles;
+  const int workers = (int)std::max(1LL, std::min(work, (long long)(device_sms() * per_sm) / g.n_cchunks));
+  dim3 grid(workers, g.n_cchunks);
+  kern<<<grid, g.threads, g.smem, st>>>(tm, w, shift, o, pool, n_img, Ho, Ho, C, same_pad_lo(H, K, S), g);
+  MT_LAUNCH_CHECK("dwconv_simt_kernel");
+  return MT_OK;
+}
+
+// smem-staged FFMA2 kernel (square feature maps, as everywhere in B0)
+int launch_dw_simt(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int C,
+                   int k, int s, cudaStream_t st) {
+  DwSimtGeom g;
+  if (!dw_simt_geom(&g, H, H, C, k, s, n_img, device_sms())) {
+    set_error("dwconv: no tile fits for h=%d c=%d k=%d s=%d", H, C, k, s);
+    return MT_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tm;
+  int rc = make_tmap_nhwc_bf16_plain(&tm, in, n_img, H, H, C, g.CW, g.IW, g.IH);
+  if (rc) return rc;
+  const int Ho = (H + s - 1) / s;
+  ProfScope prof(st, 2.0 * k * k * (double)n_img * Ho * Ho * C, (double)n_img * C * ((double)H * H + (double)Ho * Ho) * 2,
+                 "dwconv_simt k%d s%d C%d H%d", k, s, C, H);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if (k == 3 && s == 1) return launch_dw_simt_ks<3, 1>(tm, w, shift, o, pool, n_img, H, C, g, st);
+  if (k == 3 && s == 2) return launch_dw_simt_ks<3, 2>(tm, w, shift, o, pool, n_img, H, C, g, st);
+  if (k == 5 && s == 1) return launch_dw_simt_ks<5, 1>(tm, w, shift, o, pool, n_img, H, C, g, st);
+  return launch_dw_simt_ks<5, 2>(tm, w, shift, o, pool, n_img, H, C, g, st);
+}
+
+bool dw_simt_ok(int h, int w_, int c, int k, int s, const void* fused_se) {
+  return dw_umma_mode() == 3 && h == w_ && (k == 3 || k == 5) && (s == 1 || s == 2) && !fused_se;
 }
 
 int launch_dw_umma(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
@@ -496,6 +562,10 @@ int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, 
 
 int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
   // tensor-core kernels: a block sees every tile of an image -> one sum per (image, channel)
+  if (precision == MT_PREC_BF16 && dw_simt_ok(h, w_, c, k, s, nullptr)) {
+    DwSimtGeom g;
+    if (dw_simt_geom(&g, h, w_, c, k, s, 1, 148)) return g.tiles;
+  }
   if (precision == MT_PREC_BF16 && dw_umma_mode() != 2) return 1;
   return dw_geom(h, w_, c, k, s).chunks;
 }
@@ -508,6 +578,7 @@ int dwconv_dispatch(int precision, const void* in, const float* w, const float* 
   MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
   if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
   if (precision == MT_PREC_BF16) {
+    if (dw_simt_ok(h, w_, c, k, s, se.wr)) return launch_dw_simt(in, w, shift, out, pool_part, n_img, h, c, k, s, st);
     if (dw_umma_mode() == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
     if (s == 1 && h == w_ && (k == 3 || k == 5) && !se.wr && dw_umma_mode() == 1)
       return launch_dw_umma(in, w, shift, out, pool_part, n_img, h, w_, c, k, st);

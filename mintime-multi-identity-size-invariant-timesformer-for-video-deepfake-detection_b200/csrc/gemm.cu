@@ -636,6 +636,28 @@ int make_tmap_nhwc_bf16(CUtensorMap_st* m, const void* base, int n, int h, int w
   return MT_OK;
 }
 
+int make_tmap_nhwc_bf16_plain(CUtensorMap_st* m, const void* base, int n, int h, int w, int c, int box_c, int box_w,
+                              int box_h) {
+  auto enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MT_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d plain) failed (%d) n=%d h=%d w=%d c=%d box=%dx%dx%d base=%p", (int)r, n, h, w, c,
+              box_c, box_w, box_h, base);
+    return MT_ERR_DRIVER;
+  }
+  return MT_OK;
+}
+
 int launch_gemm(int precision, const GemmArgs& g, cudaStream_t stream) {
   MT_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   MT_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "gemm: N (%d) and K (%d) must be multiples of 8", g.N, g.K);

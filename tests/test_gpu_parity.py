@@ -229,7 +229,8 @@ def test_stem(prec, u8):
 
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("k,s,h,c", [(3, 1, 14, 480), (3, 2, 28, 240), (5, 1, 7, 1152), (5, 2, 14, 672), (3, 2, 112, 96),
-                                     (5, 2, 56, 144), (3, 1, 112, 32)])
+                                     (5, 2, 56, 144), (3, 1, 112, 32), (5, 1, 28, 240), (3, 1, 56, 144), (5, 1, 14, 480),
+                                     (5, 1, 14, 672), (3, 1, 7, 1152), (3, 1, 10, 24), (5, 2, 9, 8), (5, 1, 20, 136)])
 def test_dwconv_swish_pool(prec, k, s, h, c):
     n = 3
     x = rnd((n, h, h, c), 1).to(T(prec)); w = rnd((c, 1, k, k), 2, 1.0 / k); shift = rnd((c,), 3, 0.3)
