@@ -38,7 +38,9 @@ struct TcParams {
   int block_n;      // multiple of 16, <= 256 (multiple of 128 for GEGLU)
   int stages;
   int tiles_m, tiles_n;
-  int tmem_cols;    // power of two >= 2 * block_n
+  int tmem_cols;    // power of two >= acc_stages * block_n
+  int acc_stages;   // TMEM accumulator buffers (2, or 1 when two CTAs share the SM's 512 columns at block_n > 128)
+  int b_resident;   // 1: the whole weight matrix (one column tile, all k-blocks) is loaded into smem once per block
   const float* gate;
   int rows_per_gate;
   EpiParams epi;
@@ -79,8 +81,19 @@ __device__ __forceinline__ uint4* staging_piece(uint8_t* buf, int row, int piece
   return reinterpret_cast<uint4*>(buf + row * 128 + ((piece ^ (row & 7)) << 4));
 }
 
+// epilogue warps: 8 for the bf16 TMA-store epilogue (two per TMEM lane quadrant, each taking half of the
+// columns of a 64-column chunk) -- the extractor's narrow 1x1 convolutions are bound by epilogue issue
+// slots and MUFU latency, not by the MMA -- 4 for the other epilogues
+template <int KIND, bool TMA_OUT>
+constexpr int epi_warps() { return (KIND == EPI_STORE && TMA_OUT) ? 8 : 4; }
+template <int KIND, bool GATED, bool TMA_OUT>
+constexpr int tc_threads() { return 64 + 32 * epi_warps<KIND, TMA_OUT>() + (GATED ? 128 : 0); }
+
+template <int N>
+__device__ __forceinline__ void bar_sync_epi_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+
 template <typename T, int KIND, bool GATED, bool TMA_OUT>
-__global__ void __launch_bounds__(GATED ? 320 : 192, 1)
+__global__ void __launch_bounds__((tc_threads<KIND, GATED, TMA_OUT>()), (epi_warps<KIND, TMA_OUT>() == 8 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -89,14 +102,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int b_stage_bytes = p.block_n * kBlockK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages * kAStageBytes;
-  uint8_t* smem_stage = smem_b + p.stages * b_stage_bytes;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  uint8_t* smem_stage = smem_b + (p.b_resident ? num_kb : p.stages) * b_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + (TMA_OUT ? 2 * kStagingBytes : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* gated_bar = bars + 2 * kMaxStages;
   uint64_t* tmem_full = bars + 3 * kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b_full = tmem_empty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [N] (8-warp epilogue only)
+  constexpr int kEW = epi_warps<KIND, TMA_OUT>();
+  constexpr int kGateThread0 = 64 + 32 * kEW;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,9 +128,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::mbar_init(&empty_bar[s], 1);
       ptx::mbar_init(&gated_bar[s], 128);
     }
+    ptx::mbar_init(b_full, 1);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 128);
+      // 8-warp epilogue: one arrival per warp; 4 warps own a buffer when there are two buffers, else all 8
+      ptx::mbar_init(&tmem_empty[s], kEW == 8 ? (p.acc_stages == 2 ? 4 : 8) : 128);
     }
     ptx::fence_mbar_init();
   }
@@ -120,19 +140,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
+  if (kEW == 8) {
+    // bias (BN shift) staged once per block; pre-halved when the swish follows (silu2 takes shift/2)
+    const float bs = p.epi.act == 1 ? 0.5f : 1.0f;
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) bias_s[i] = p.epi.bias ? p.epi.bias[i] * bs : 0.f;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       PipeState ps;
-      const uint32_t tx_bytes = (uint32_t)(kAStageBytes + b_stage_bytes);
+      // The extractor's early 1x1 convolutions have a weight matrix of a few KiB: re-fetching it for every
+      // 128-row tile makes every SM hammer the same handful of L2 lines (measured: 250 of 580 us at N=96,
+      // K=16), so it is loaded ONCE per block when it fits.
+      if (p.b_resident) {
+        ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(num_kb * b_stage_bytes));
+        for (int kb = 0; kb < num_kb; ++kb)
+          ptx::tma_load_2d(smem_b + kb * b_stage_bytes, &tmap_b, b_full, kb * kBlockK, 0);
+      }
+      const uint32_t tx_bytes = (uint32_t)(kAStageBytes + (p.b_resident ? 0 : b_stage_bytes));
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.tiles_n) * kBlockM;
         const int n0 = (tile % p.tiles_n) * p.block_n;
@@ -140,7 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
           ptx::tma_load_2d(smem_a + ps.stage * kAStageBytes, &tmap_a, &full_bar[ps.stage], kb * kBlockK, m0);
-          ptx::tma_load_2d(smem_b + ps.stage * b_stage_bytes, &tmap_b, &full_bar[ps.stage], kb * kBlockK, n0);
+          if (!p.b_resident)
+            ptx::tma_load_2d(smem_b + ps.stage * b_stage_bytes, &tmap_b, &full_bar[ps.stage], kb * kBlockK, n0);
           ps.advance(p.stages);
         }
       }
@@ -151,10 +184,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       PipeState ps;
       const uint32_t idesc = ptx::umma_idesc_bf16_f32(kBlockM, (uint32_t)p.block_n);
+      if (p.b_resident) ptx::mbar_wait(b_full, 0);
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = p.acc_stages == 2 ? (it & 1) : 0;
+        const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
@@ -162,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::mbar_wait(GATED ? &gated_bar[ps.stage] : &full_bar[ps.stage], ps.phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem_a + ps.stage * kAStageBytes);
-          const uint32_t b_addr = ptx::smem_u32(smem_b + ps.stage * b_stage_bytes);
+          const uint32_t b_addr = ptx::smem_u32(smem_b + (p.b_resident ? kb : ps.stage) * b_stage_bytes);
           const int k_left = p.K - kb * kBlockK;
           const int ksteps = k_left >= kBlockK ? 4 : (k_left + 15) / 16;  // TMA zero-filled the K tail
           for (int k = 0; k < ksteps; ++k) {
@@ -177,7 +211,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (kEW == 8 && warp < 10) {
+    // ===================================================================== epilogue (8 warps, bf16 TMA store)
+    // No block-wide barriers: a warp owns the 32 accumulator rows of its TMEM lane quadrant.  With two
+    // accumulator buffers the two warps of a quadrant take alternate TILES (one warp set per buffer: two
+    // independent MMA -> epilogue pipelines per block); with one buffer they split the tile's 32-column units.
+    // Per unit: tcgen05.ld -> BN shift / swish / skip in registers -> its own 2 KiB staging slab (64-byte
+    // swizzle) -> its own TMA store of a 32 x 32 box.  Slabs are double buffered per warp.
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;
+    const int trow = quad * 32 + lane;
+    const EpiParams& e = p.epi;
+    const bool act = e.act == 1;
+    const bf16* resid = reinterpret_cast<const bf16*>(e.resid);
+    uint8_t* slab = smem_stage + (warp - 2) * 4096;          // 2 x 2 KiB
+    const int n_units = (p.block_n + 31) >> 5;
+    uint32_t store_it = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = p.acc_stages == 2 ? (it & 1) : 0;
+      const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
+      if (p.acc_stages == 2 && as != half) continue;
+      const int m0 = (tile / p.tiles_n) * kBlockM;
+      const int n0 = (tile % p.tiles_n) * p.block_n;
+      const int row = m0 + trow;
+      ptx::mbar_wait(&tmem_full[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
+      const int u0 = p.acc_stages == 2 ? 0 : ((half + it) & 1), ustep = p.acc_stages == 2 ? 1 : 2;
+      for (int u = u0; u < n_units; u += ustep) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + u * 32, r);
+        uint8_t* stg = slab + (store_it & 1) * 2048;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab's previous store drained
+        __syncwarp();
+        ptx::tmem_ld_wait();
+        const int col = n0 + u * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float2 v[4];
+          if (col + g * 8 < p.N) {                 // (N is a multiple of 8)
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + g * 8 + 4);
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 x = make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1]));
+              if (act) {                           // swish(x + shift): h = x/2 + shift/2, h + h*tanh(h)
+                const float2 h = __ffma2_rn(x, make_float2(0.5f, 0.5f), bb[i]);
+                float2 t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+                v[i] = __ffma2_rn(h, t, h);
+              } else {
+                v[i] = __fadd2_rn(x, bb[i]);
+              }
+            }
+            if (resid != nullptr && row < p.M) {    // MBConv skip connection (model.py:123-127), added after BN
+              const uint4 q = *reinterpret_cast<const uint4*>(resid + (size_t)row * e.ldo + col + g * 8);
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                v[i] = __fadd2_rn(v[i], make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u)));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = make_float2(0.f, 0.f);
+          }
+          // 64-byte swizzle: 16-byte piece g of row `lane` sits at piece g ^ ((lane >> 1) & 3)
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y),
+                         pack_bf16(v[3].x, v[3].y));
+        }
+        ptx::fence_proxy_async_smem();             // slab writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(ptx::smem_u32(stg)), "r"(col), "r"(m0 + quad * 32)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++store_it;
+      }
+      // all TMEM reads of this warp for the tile have completed (tcgen05.wait::ld above): hand it back
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[as]);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+  } else if (kEW == 4 && warp < 6) {
     // ===================================================================== epilogue (4 warps)
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
     const int trow = quad * 32 + lane;             // row of the tile this thread owns
@@ -185,8 +309,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t store_it = 0;                         // staging buffer ring position (TMA_OUT)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = p.acc_stages == 2 ? (it & 1) : 0;
+      const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
       const int m0 = (tile / p.tiles_n) * kBlockM;
       const int n0 = (tile % p.tiles_n) * p.block_n;
       const int row = m0 + trow;
@@ -318,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================================================== SE-gate warps (4 warps)
     // Multiply the freshly landed A tile by gate[image(row)][k] in shared memory (reference
     // model.py:115: x = sigmoid(se) * x, ahead of the project conv), then hand it to the MMA warp.
-    const int r = threadIdx.x - 192;  // tile row 0..127
+    const int r = threadIdx.x - kGateThread0;  // tile row 0..127
     PipeState ps;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * kBlockM;
@@ -327,9 +451,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) {
         // the gate values do not depend on the tile: fetch them BEFORE waiting for the TMA so their L2
         // latency overlaps the load instead of sitting on the TMA -> gate -> MMA critical path
-        float4 gv[16];
+        // (first half of the row's gates only: registers are shared with 8 epilogue warps at 2 blocks per SM)
+        float4 gv[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           const int k = kb * kBlockK + c * 8;
           if (k < p.K) {
             gv[2 * c] = *reinterpret_cast<const float4*>(grow + k);
@@ -339,19 +464,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
         uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int k = kb * kBlockK + c * 8;
-          if (k < p.K) {
-            uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
-            uint4 u = *ptr;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-            const float4 g0 = gv[2 * c], g1 = gv[2 * c + 1];
-            float2 f;
-            f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
-            f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
-            f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
-            f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
-            *ptr = u;
+        for (int hb = 0; hb < 2; ++hb) {
+          if (hb == 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int k = kb * kBlockK + 32 + c * 8;
+              if (k < p.K) {
+                gv[2 * c] = *reinterpret_cast<const float4*>(grow + k);
+                gv[2 * c + 1] = *reinterpret_cast<const float4*>(grow + k + 4);
+              }
+            }
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int c = hb * 4 + c4;
+            const int k = kb * kBlockK + c * 8;
+            if (k < p.K) {
+              uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
+              uint4 u = *ptr;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              const float4 g0 = gv[2 * c4], g1 = gv[2 * c4 + 1];
+              float2 f;
+              f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
+              f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
+              f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
+              f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
+              *ptr = u;
+            }
           }
         }
         ptx::fence_proxy_async_smem();
@@ -478,7 +617,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2D row-major [rows][cols] tensor (row pitch = pitch_elems), box = [box_rows][128 bytes of columns],
 // 128-byte swizzle, zero fill / clipping out of bounds.
-int make_tmap_2d(CUtensorMap* m, const void* base, bool f32, int rows, int cols, int pitch_elems, int box_rows) {
+int make_tmap_2d(CUtensorMap* m, const void* base, bool f32, int rows, int cols, int pitch_elems, int box_rows,
+                 int box_bytes = 128) {
   auto enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -487,11 +627,12 @@ int make_tmap_2d(CUtensorMap* m, const void* base, bool f32, int rows, int cols,
   const int es = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * es};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(box_bytes / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d pitch=%d box_rows=%d base=%p", (int)r, rows, cols,
               pitch_elems, box_rows, base);
@@ -530,13 +671,23 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   p.block_n = bn;
   p.tiles_m = (g.M + kBlockM - 1) / kBlockM;
   p.tiles_n = (g.N + bn - 1) / bn;
+  constexpr int kEW = epi_warps<KIND, TMA_OUT>();
+  const int num_kb = (g.K + kBlockK - 1) / kBlockK;
+  const int b_block = bn * kBlockK * 2;
+  p.b_resident = (p.tiles_n == 1 && num_kb * b_block <= 40 * 1024) ? 1 : 0;
+  const int stage_bytes = kAStageBytes + (p.b_resident ? 0 : b_block);
+  const int bias_bytes = kEW == 8 ? ((g.N * 4 + 15) & ~15) : 0;
+  const int fixed = (TMA_OUT ? 2 * kStagingBytes : 0) + 1024 /*align slack*/ + (3 * kMaxStages + 5) * 8 + 16 + bias_bytes +
+                    (p.b_resident ? num_kb * b_block : 0);
+  // two blocks per SM (2 x (112 KiB + 1 KiB reserved) <= 228 KiB, 2 x 256 TMEM columns) whenever the tile is at
+  // most 128 wide, and for the 8-warp epilogue also up to 256 wide when K fits one k-block: the accumulator is
+  // then single buffered and the other block's epilogue covers the MMA latency
+  const bool wide_pair = kEW == 8 && bn > 128 && num_kb == 1 && 2 * stage_bytes + fixed <= 112 * 1024;
+  const int ctas_per_sm = (bn <= 128 || wide_pair) ? 2 : 1;
+  p.acc_stages = (ctas_per_sm == 2 && bn > 128) ? 1 : 2;
   int tmem = 32;
-  while (tmem < 2 * bn) tmem <<= 1;
+  while (tmem < p.acc_stages * bn) tmem <<= 1;
   p.tmem_cols = tmem;
-  const int stage_bytes = kAStageBytes + bn * kBlockK * 2;
-  const int fixed = (TMA_OUT ? 2 * kStagingBytes : 0) + 1024 /*align slack*/ + (3 * kMaxStages + 4) * 8 + 16;
-  // <=128-wide tiles leave room for 2 CTAs per SM (2 x (112 KiB + 1 KiB reserved) <= 228 KiB)
-  const int ctas_per_sm = bn <= 128 ? 2 : 1;
   const int budget = (ctas_per_sm == 2 ? 112 : 226) * 1024 - fixed;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -552,7 +703,8 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   if (TMA_OUT) {
     const bool f32 = KIND == EPI_RESID_F32;
     const int out_cols = KIND == EPI_GEGLU ? g.N / 2 : g.N;
-    rc = make_tmap_2d(&tout, g.epi.out, f32, g.M, out_cols, g.epi.ldo, kBlockM);
+    if (kEW == 8) rc = make_tmap_2d(&tout, g.epi.out, false, g.M, out_cols, g.epi.ldo, 32, 64);   // per-warp 32 x 32 boxes
+    else rc = make_tmap_2d(&tout, g.epi.out, f32, g.M, out_cols, g.epi.ldo, kBlockM);
     if (rc) return rc;
   } else {
     tout = ta;
@@ -567,7 +719,7 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   }
   int grid = p.tiles_m * p.tiles_n;
   if (grid > num_sms() * ctas_per_sm) grid = num_sms() * ctas_per_sm;
-  kern<<<grid, GATED ? 320 : 192, smem, stream>>>(ta, tb, tout, p);
+  kern<<<grid, tc_threads<KIND, GATED, TMA_OUT>(), smem, stream>>>(ta, tb, tout, p);
   MT_LAUNCH_CHECK("gemm_tc_kernel");
   return MT_OK;
 }
@@ -590,7 +742,7 @@ int launch_tc(const GemmArgs& g, cudaStream_t stream) {
     if (tc2_enabled() && tc2_eligible(g)) return launch_tc2<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
   }
   // per-row gathers (skip connection, embedding rows) use the direct epilogue; everything else TMA
-  if (KIND == EPI_PATCH_EMBED || (KIND == EPI_STORE && g.epi.resid)) return launch_tc_impl<KIND, GATED, false>(g, stream);
+  if (KIND == EPI_PATCH_EMBED) return launch_tc_impl<KIND, GATED, false>(g, stream);
   if ((g.epi.ldo * (KIND == EPI_RESID_F32 ? 4 : 2)) % 16 != 0 || (reinterpret_cast<uintptr_t>(g.epi.out) & 15))
     return launch_tc_impl<KIND, GATED, false>(g, stream);
   return launch_tc_impl<KIND, GATED, true>(g, stream);
