@@ -160,10 +160,14 @@ int mt_layernorm_fwd(int precision, const float* x, const float* gamma, const fl
  *   qkv T [B][1+f*n][3*heads*dim_head] -> out T [B][1+f*n][heads*dim_head] (heads merged, before to_out)
  *   mode MT_ATTN_TIME : groups (b,h,patch): frames attend frames (+CLS key), bias = mask[b][k] & identities_mask[b][q][k]
  *   mode MT_ATTN_SPACE: groups (b,h,frame): patches attend patches (+CLS key), no mask
- *   CLS row: attends all tokens with the padded-frame mask; cls_attn f32 [B*heads][1+f*n] (may be NULL). */
+ *   CLS row: attends all tokens with the padded-frame mask; cls_attn f32 [B*heads][1+f*n] (may be NULL).
+ *   workspace: mt_divided_attn_workspace_bytes(batch, f, n, heads) bytes, 16-byte aligned; the bf16 path keeps the
+ *   per-group partials of the CLS row there (computed inside the grouped kernels, merged by a small combine
+ *   kernel).  NULL selects the stand-alone CLS-row kernel (always used by the fp32 path). */
+size_t mt_divided_attn_workspace_bytes(int batch, int f, int n, int heads);
 int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t* mask, const uint8_t* identities_mask,
                         int mode, void* out, float* cls_attn, int batch, int f, int n, int heads, int dim_head,
-                        void* stream);
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stem: ZeroPad2d(0,1,0,1) + conv 3x3 s2 (3->32) + BN + swish (utils.py:248-276, model.py:276)
  *   x NHWC [n_img][H][W][3] (f32/u8) -> out T NHWC [n_img][H/2][W/2][32] */

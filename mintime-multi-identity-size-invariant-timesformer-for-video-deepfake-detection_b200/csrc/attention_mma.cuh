@@ -127,11 +127,148 @@ __device__ __forceinline__ void attend_mtile(uint8_t* qs, uint8_t* ks, uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CLS row of Attention.forward (:117-120): query 0 of each (b, h) attends ALL N keys with the padded-frame
+// mask (cls_attn_mask :258-260).  The grouped kernels already hold every patch key/value of their group in
+// shared memory, so ONE extra warp per group computes the CLS query's flash-style partial over those keys
+//   m = max_k s_k,  l = sum_k exp(s_k - m),  o[d] = sum_k exp(s_k - m) v[k][d]       (s_k = q0 . k_k)
+// (and the raw scores for the attention map) and cls_combine_kernel merges the groups + the CLS key itself:
+// qkv is not streamed a second time for the CLS row.  Keys = rows 1 .. nk of the ks / vs tiles.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kClsStride = 66;                   // floats per partial: m, l, o[64]
+
+// MTK = 16-key tiles covering the nk keys; `es` = 16*MTK floats of per-warp scratch; q0 = the CLS query (global,
+// bf16, 64 values); rows beyond `max_row` are never addressed (rows past the keys are zero-filled tiles).
+// Both products run on mma.sync: scores = K q0 (K rows as the A operand, q0 broadcast over the 8 B columns),
+// o = e^T V (e broadcast over the 16 A rows, V through ldmatrix.trans exactly as in attend_mtile).
+template <int MTK, typename Valid, typename Token>
+__device__ __forceinline__ void cls_partial_warp(uint8_t* ks, uint8_t* vs, const bf16* q0, float* es, int nk, int max_row,
+                                                 int lane, Valid valid, Token token_of, float* part, float* scores) {
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t qb[4][2];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    qb[kk][0] = *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 2 * t);
+    qb[kk][1] = *reinterpret_cast<const uint32_t*>(q0 + kk * 16 + 2 * t + 8);
+  }
+  float s[MTK][2];
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int mt = 0; mt < MTK; ++mt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int row = min(1 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, max_row);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      ldmatrix_x4(a, smem_u32(tile_ptr(ks, row, kk * 2 + (lane >> 4))));
+      mma_bf16(acc, a, qb[kk][0], qb[kk][1]);
+    }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {             // this lane: keys mt*16 + g (c0) and + 8 (c2)
+      const int k = mt * 16 + g + hr * 8;
+      float v = -FLT_MAX;
+      if (k < nk) {
+        if (valid(k)) v = acc[hr * 2];           // masked_fill(~mask, -finfo.max) (:83-84)
+        if (scores && t == 0) scores[token_of(k)] = v;
+      }
+      s[mt][hr] = v;
+      m = fmaxf(m, v);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float l = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < MTK; ++mt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const float e = s[mt][hr] > -FLT_MAX ? __expf(s[mt][hr] - m) : 0.f;   // (all keys masked: l = 0)
+      l += e;
+      if (t == 0) es[mt * 16 + g + hr * 8] = e;
+    }
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  __syncwarp();
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < MTK; ++kk) {
+    uint32_t a[4];
+    a[0] = a[1] = pack2(es[kk * 16 + 2 * t], es[kk * 16 + 2 * t + 1]);
+    a[2] = a[3] = pack2(es[kk * 16 + 2 * t + 8], es[kk * 16 + 2 * t + 9]);
+    const int row = min(1 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, max_row);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, smem_u32(tile_ptr(vs, row, dp * 2 + (lane >> 4))));
+      mma_bf16(o[dp * 2], a, b[0], b[1]);
+      mma_bf16(o[dp * 2 + 1], a, b[2], b[3]);
+    }
+  }
+  if (lane == 0) { part[0] = m; part[1] = l; }
+  if (g == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(part + 2 + j * 8 + 2 * t) = make_float2(o[j][0], o[j][1]);
+  }
+}
+
+// Merge of the per-group partials with the CLS key itself; one block (64 threads) per (b, h).
+// Writes the CLS row of `out` and, when `cls_attn` is given (it holds the raw scores of the patch keys),
+// normalises it in place into the attention map the model returns (:271).
+static __global__ void __launch_bounds__(64) cls_combine_kernel(const bf16* __restrict__ qkv, const float* __restrict__ parts,
+                                                                bf16* __restrict__ out, float* __restrict__ cls_attn,
+                                                                int N, int G, int heads) {
+  __shared__ float red[2];
+  __shared__ __align__(16) float ps[64 * kClsStride];            // the (b, h)'s partials (G <= 63)
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int inner = heads * 64, ld = 3 * inner;
+  const bf16* base = qkv + (size_t)b * N * ld + h * 64;
+  const int d = threadIdx.x;
+  {                                              // all loads independent: one L2 round trip, not one per group
+    const float2* src = reinterpret_cast<const float2*>(parts + (size_t)bh * G * kClsStride);
+    float2* dst = reinterpret_cast<float2*>(ps);
+    for (int i = d; i < G * (kClsStride / 2); i += 64) dst[i] = src[i];
+  }
+  float p = __bfloat162float(base[d]) * __bfloat162float(base[inner + d]);     // q0 . k0
+  const float v0 = __bfloat162float(base[2 * inner + d]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  if ((d & 31) == 0) red[d >> 5] = p;
+  __syncthreads();
+  const float s0 = red[0] + red[1];
+  float M = s0;
+  for (int g = 0; g < G; ++g)
+    if (ps[g * kClsStride + 1] > 0.f) M = fmaxf(M, ps[g * kClsStride]);
+  const float e0 = expf(s0 - M);
+  float L = e0, acc = e0 * v0;
+  for (int g = 0; g < G; ++g) {                  // fixed order: deterministic
+    const float lg = ps[g * kClsStride + 1];
+    if (lg > 0.f) {
+      const float w = expf(ps[g * kClsStride] - M);
+      L = fmaf(w, lg, L);
+      acc = fmaf(w, ps[g * kClsStride + 2 + d], acc);
+    }
+  }
+  const float inv = 1.0f / L;
+  out[(size_t)b * N * inner + h * 64 + d] = __float2bfloat16_rn(acc * inv);
+  if (cls_attn) {
+    float* row = cls_attn + (size_t)bh * N;
+    for (int j = d; j < N; j += 64) {
+      const float sj = j == 0 ? s0 : row[j];
+      row[j] = sj > -FLT_MAX ? expf(sj - M) * inv : 0.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // SPACE: one block (4 warps) per group (b, h, frame): 49 queries x (CLS + 49) keys, no mask (:266).
 // ---------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(128) attn_space_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int f,
-                                                             int n, int heads) {
+// A fifth warp computes the group's partial of the CLS row (cls_partial_warp).
+static __global__ void __launch_bounds__(160) attn_space_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mask,
+                                                             bf16* __restrict__ out, float* __restrict__ cls_parts,
+                                                             float* __restrict__ cls_scores, int f, int n, int heads) {
   __shared__ __align__(1024) uint8_t sm[3 * 64 * 128];
+  __shared__ float es[64];
   uint8_t* qs = sm;
   uint8_t* ks = sm + 64 * 128;
   uint8_t* vs = sm + 2 * 64 * 128;
@@ -142,7 +279,7 @@ static __global__ void __launch_bounds__(128) attn_space_mma_kernel(const bf16* 
   const bf16* base = qkv + (size_t)b * N * ld + h * 64;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tok0 = 1 + fr * n;                   // first patch token of the frame
-  for (int e = tid; e < 64 * 8; e += 128) {
+  for (int e = tid; e < 64 * 8; e += 160) {
     const int r = e >> 3, c = e & 7;
     // queries: row r = patch r; keys/values: row 0 = CLS, row r = patch r-1
     if (r < n) cp_async16(tile_ptr(qs, r, c), base + (size_t)(tok0 + r) * ld + c * 8);
@@ -159,7 +296,13 @@ static __global__ void __launch_bounds__(128) attn_space_mma_kernel(const bf16* 
   cp_async_wait_all();
   __syncthreads();
   const int nk = n + 1;
-  if (warp * 16 < n) {
+  if (warp == 4) {
+    const int bh = b * heads + h;
+    const bool frame_ok = mask[b * f + fr] != 0;
+    // (base = token 0's q for this head: the CLS query, already scaled by dim_head^-1/2 through the weights)
+    cls_partial_warp<4>(ks, vs, base, es, n, 63, lane, [&](int) { return frame_ok; }, [&](int k) { return tok0 + k; },
+                        cls_parts + ((size_t)bh * f + fr) * kClsStride, cls_scores ? cls_scores + (size_t)bh * N : nullptr);
+  } else if (warp * 16 < n) {
     attend_mtile<4>(qs, ks, vs, warp * 16, lane, [&](int, int key) { return key < nk; });
     // rows warp*16 .. +15 of qs now hold O; 8 lanes write one 128-byte row
     for (int e = lane; e < 16 * 8; e += 32) {
@@ -176,20 +319,30 @@ static __global__ void __launch_bounds__(128) attn_space_mma_kernel(const bf16* 
 // key k allowed iff mask[b][k] & identities_mask[b][q][k]; the CLS key always.  4 groups per block.
 // NKT = ceil((f + 1) / 16) key tiles, MT = ceil(f / 16) query tiles.
 // ---------------------------------------------------------------------------------------------------
+// Warps 4-7 compute the CLS-row partials of the groups of warps 0-3 (cls_partial_warp).
 template <int NKT, int MT>
-__global__ void __launch_bounds__(128) attn_time_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mask,
+__global__ void __launch_bounds__(256) attn_time_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ mask,
                                                             const uint8_t* __restrict__ idmask, bf16* __restrict__ out,
+                                                            float* __restrict__ cls_parts, float* __restrict__ cls_scores,
                                                             int f, int n, int heads) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   constexpr int kQBytes = MT * 16 * 128, kKBytes = NKT * 16 * 128;
   constexpr int kWarpBytes = kQBytes + 2 * kKBytes;
   __shared__ unsigned long long allow_bits[64];  // per query frame: bit k set <=> key k (0 = CLS) allowed
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float es_all[4][16 * NKT];
+  __shared__ uint8_t frame_ok[64];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool cls_warp = tid >= 128;
+  const int warp = (tid >> 5) & 3;               // group slot; warps 4-7 mirror warps 0-3
   // blocks are laid out per (b, h): ceil(n / 4) blocks each, one warp per patch position
   const int blocks_per_bh = (n + 3) / 4;
   const int bh = blockIdx.x / blocks_per_bh;
   const int p = (blockIdx.x % blocks_per_bh) * 4 + warp;
   const int b = bh / heads, h = bh % heads;
+  if (tid >= 128 && tid < 192) {
+    const int d = tid - 128;
+    frame_ok[d] = d < f ? mask[b * f + d] : 0;
+  }
   if (tid < 64) {
     unsigned long long bits = 1ull;              // CLS key
     if (tid < f)
@@ -203,7 +356,7 @@ __global__ void __launch_bounds__(128) attn_time_mma_kernel(const bf16* __restri
   const int N = 1 + f * n, inner = heads * 64, ld = 3 * inner;
   const bf16* base = qkv + (size_t)b * N * ld + h * 64;
   const bool active = p < n;
-  if (active) {
+  if (active && !cls_warp) {
     for (int e = lane; e < MT * 16 * 8; e += 32) {
       const int r = e >> 3, c = e & 7;
       if (r < f) cp_async16(tile_ptr(qs, r, c), base + (size_t)(1 + r * n + p) * ld + c * 8);
@@ -224,6 +377,12 @@ __global__ void __launch_bounds__(128) attn_time_mma_kernel(const bf16* __restri
   cp_async_wait_all();
   __syncthreads();                               // allow_bits + (per-warp) tiles visible
   if (!active) return;
+  if (cls_warp) {                                // keys of this group: frame k at patch p -> token 1 + k*n + p
+    cls_partial_warp<NKT>(ks, vs, base, es_all[warp], f, NKT * 16 - 1, lane, [&](int k) { return frame_ok[k] != 0; },
+                          [&](int k) { return 1 + k * n + p; }, cls_parts + ((size_t)bh * n + p) * kClsStride,
+                          cls_scores ? cls_scores + (size_t)bh * N : nullptr);
+    return;
+  }
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     attend_mtile<NKT>(qs, ks, vs, mt * 16, lane, [&](int ql, int key) {

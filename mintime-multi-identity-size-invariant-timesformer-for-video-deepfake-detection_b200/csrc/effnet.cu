@@ -91,6 +91,131 @@ __global__ void __launch_bounds__(128) stem_kernel(const TIN* __restrict__ x, co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// stem on tensor cores (bf16 path): the 3x3x3 stencil is a K = 27 contraction -- per output pixel 864 FMAs
+// on the CUDA cores (the FFMA kernel above is issue bound at 0.47 ms / 512 images) or 2 k-steps x 4 n-tiles of
+// mma.sync m16n8k16 per 16 pixels.  A block stages the 2*TH+1 input rows of TH output rows in shared memory
+// as bf16 (pixel values 0..255 are exact in bf16); with K ordered (ky, j = kx*3+ci padded to 10) the A
+// fragment of a pixel is three contiguous 9-element runs of those rows, so it is read with plain 32-bit
+// shared loads -- no im2col buffer.  Weights are bf16-rounded (B fragments in registers), accumulation
+// fp32, BN shift + swish in the epilogue, output staged per warp for 512-byte coalesced stores.
+// Requires W % 16 == 0 and an even H (TF-SAME pad_lo = 0); other shapes take the FFMA kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStemTH = 8;        // output rows per block
+constexpr int kStemRS = 688;      // shared-memory row pitch in elements (>= 224*3 + 10, multiple of 8)
+
+__device__ __forceinline__ void stem_cvt_store(bf16* dst, const float* src) {     // 8 values
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(attn::pack2(a.x, a.y), attn::pack2(a.z, a.w), attn::pack2(b.x, b.y),
+                                              attn::pack2(b.z, b.w));
+}
+__device__ __forceinline__ void stem_cvt_store(bf16* dst, const uint8_t* src) {   // 8 values
+  const uint2 u = *reinterpret_cast<const uint2*>(src);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w = i < 2 ? u.x : u.y;
+    const uint32_t lo = (w >> ((i & 1) * 16)) & 0xffu, hi = (w >> ((i & 1) * 16 + 8)) & 0xffu;
+    o[i] = attn::pack2((float)lo, (float)hi);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <typename TIN>
+__global__ void __launch_bounds__(256) stem_tc_kernel(const TIN* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ shift, bf16* __restrict__ out, int H,
+                                                      int W, int Ho, int Wo) {
+  __shared__ __align__(16) bf16 rows[(2 * kStemTH + 1) * kStemRS];
+  __shared__ __align__(16) uint8_t ostage[8][16 * 64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int img = blockIdx.y, oy0 = blockIdx.x * kStemTH;
+  // ---- B fragments: k = ky*10 + j, j = kx*3 + ci (j = 9 and k >= 30 are zero rows); n = nt*8 + g
+  uint32_t bfr[2][4][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        float wv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kk = ks * 16 + hi * 8 + 2 * t + e;
+          const int ky = kk / 10, j = kk - ky * 10;
+          wv[e] = (ky < 3 && j < 9) ? w[(ky * 9 + j) * 32 + nt * 8 + g] : 0.f;
+        }
+        bfr[ks][nt][hi] = attn::pack2(wv[0], wv[1]);
+      }
+  // per-lane element offsets of the A fragment pairs (k even -> j even -> 4-byte aligned)
+  int aoff[2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      int kk = ks * 16 + hi * 8 + 2 * t;
+      if (kk >= 30) kk = 28;                       // zero weights: any finite value will do
+      const int ky = kk / 10;
+      aoff[ks][hi] = ky * kStemRS + (kk - ky * 10);
+    }
+  float2 hsh[4];                                   // BN shift / 2 for columns nt*8 + 2t, +1
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) hsh[nt] = make_float2(0.5f * shift[nt * 8 + 2 * t], 0.5f * shift[nt * 8 + 2 * t + 1]);
+
+  // ---- stage the input rows 2*oy0 .. 2*oy0 + 2*TH (zero beyond the image: TF-SAME pads bottom / right)
+  const int row_elems = W * 3;
+  for (int i = tid; i < (2 * kStemTH + 1) * (kStemRS / 8); i += 256) {
+    const int r = i / (kStemRS / 8), e = (i - r * (kStemRS / 8)) * 8;
+    const int iy = 2 * oy0 + r;
+    bf16* dst = rows + r * kStemRS + e;
+    if (iy < H && e < row_elems) stem_cvt_store(dst, x + ((size_t)img * H + iy) * row_elems + e);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+
+  const int mt_per_row = (Wo + 15) / 16;
+  uint8_t* stg = ostage[warp];
+  for (int mt = warp; mt < kStemTH * mt_per_row; mt += 8) {
+    const int oyl = mt / mt_per_row, ox0 = (mt - oyl * mt_per_row) * 16;
+    const int oy = oy0 + oyl;
+    if (oy >= Ho) break;
+    const bf16* base = rows + (2 * oyl) * kStemRS + 6 * (ox0 + g);
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(base + aoff[ks][0]);
+      a[1] = *reinterpret_cast<const uint32_t*>(base + 48 + aoff[ks][0]);      // pixel + 8
+      a[2] = *reinterpret_cast<const uint32_t*>(base + aoff[ks][1]);
+      a[3] = *reinterpret_cast<const uint32_t*>(base + 48 + aoff[ks][1]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) attn::mma_bf16(acc[nt], a, bfr[ks][nt][0], bfr[ks][nt][1]);
+    }
+    // epilogue: rows g / g+8, columns nt*8 + 2t, +1 -> per-warp staging (16 px x 64 B, 16-byte chunks swizzled)
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int px = g + hr * 8;
+        const float2 v = silu2(make_float2(acc[nt][hr * 2], acc[nt][hr * 2 + 1]), hsh[nt]);
+        *reinterpret_cast<uint32_t*>(stg + px * 64 + ((nt ^ ((px >> 1) & 3)) << 4) + 4 * t) = attn::pack2(v.x, v.y);
+      }
+    }
+    __syncwarp();
+    bf16* orow = out + (((size_t)img * Ho + oy) * Wo + ox0) * 32;
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int px = (lane >> 2) + hr * 8, c = lane & 3;
+      if (ox0 + px < Wo)
+        *reinterpret_cast<uint4*>(orow + px * 32 + c * 8) =
+            *reinterpret_cast<const uint4*>(stg + px * 64 + ((c ^ ((px >> 1) & 3)) << 4));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // depthwise kxk stride s + BN + swish, and per-(image, chunk, channel) partial sums for the
 // squeeze-excite average pool (model.py:105-107,110).
 //
@@ -291,76 +416,107 @@ __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, c
 
 // ---------------------------------------------------------------------------------------------------
 // SE excitation (model.py:110-115): mean = sum_chunks(pool_part)/hw; gate = sigmoid(We*swish(Wr*mean+br)+be).
-// One block handles kSeImgs images so the two small weight matrices are streamed from L2 once per
-// kSeImgs images; `we_t` is the expand weight transposed to [SQ][C] (lanes read consecutive channels).
+// The arithmetic is tiny (2*SQ*C MACs per image); what costs is streaming the two weight matrices
+// (up to 2 x 48 x 1152 floats) from L2, so one block handles kSeImgs images and every weight it loads feeds
+// kSeImgs FMAs.  `we_t` is the expand weight transposed to [SQ][C] (lanes read consecutive channels).
+// Fixed reduction orders: deterministic.
 // ---------------------------------------------------------------------------------------------------
-// One block per image.  The work is tiny (2*SQ*C MACs); what matters is memory-level parallelism on the
-// weight reads from L2: each warp owns a slice of the channels and walks all SQ rows with independent,
-// coalesced loads (phase 2), each thread owns channels and walks all SQ rows (phase 3).
+constexpr int kSeImgs = 4;
 __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int n_chunks, float inv_hw,
                                                       const float* __restrict__ wr, const float* __restrict__ br,
                                                       const float* __restrict__ we_t, const float* __restrict__ be,
                                                       float* __restrict__ gate, int n_img, int C, int SQ) {
-  extern __shared__ float sm[];
-  float* mean = sm;                  // [C]
-  float* sq = sm + C;                // [SQ]
-  float* part = sq + SQ;             // [8][SQ]
-  const int img = blockIdx.x;
+  extern __shared__ __align__(16) float sm[];
+  float* mean = sm;                      // [kSeImgs][C]
+  float* sq = sm + kSeImgs * C;          // [kSeImgs][SQ]
+  const int img0 = blockIdx.x * kSeImgs;
+  const int n_here = min(kSeImgs, n_img - img0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int c = tid; c < C; c += 256) {
-    double acc = 0.0;                // fixed order, double: deterministic and as accurate as the reference's mean
-    for (int j = 0; j < n_chunks; ++j) acc += (double)pool_part[((size_t)img * n_chunks + j) * C + c];
-    mean[c] = (float)(acc * (double)inv_hw);
+  for (int i = tid; i < kSeImgs * C; i += 256) {
+    const int g = i / C, c = i - g * C;
+    double acc = 0.0;                    // fixed order, double: deterministic and as accurate as the reference's mean
+    if (g < n_here) {
+      const float* pp = pool_part + (size_t)(img0 + g) * n_chunks * C + c;
+      int j = 0;
+      for (; j + 8 <= n_chunks; j += 8) {  // 8 independent loads in flight (the per-tile partials of dwconv_simt)
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = pp[(size_t)(j + u) * C];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += (double)v[u];
+      }
+      for (; j < n_chunks; ++j) acc += (double)pp[(size_t)j * C];
+    }
+    mean[i] = (float)(acc * (double)inv_hw);
   }
   __syncthreads();
-  // phase 2: s[j] = swish(br[j] + sum_c wr[j][c] * mean[c]); warp w covers channels [c_lo, c_hi)
-  const int per_warp = ((C + 7) / 8 + 31) / 32 * 32;
-  const int c_lo = warp * per_warp, c_hi = min(C, c_lo + per_warp);
-  for (int j0 = 0; j0 < SQ; j0 += 4) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int c = c_lo + lane; c < c_hi; c += 32) {
-      const float m = mean[c];
-      const float* wp = wr + (size_t)j0 * C + c;
-      a0 = fmaf(wp[0], m, a0);
-      if (j0 + 1 < SQ) a1 = fmaf(wp[C], m, a1);
-      if (j0 + 2 < SQ) a2 = fmaf(wp[2 * (size_t)C], m, a2);
-      if (j0 + 3 < SQ) a3 = fmaf(wp[3 * (size_t)C], m, a3);
+  // phase 2: s[g][j] = swish(br[j] + sum_c wr[j][c] * mean[g][c]); one warp per squeeze row j.  The row is
+  // fetched as up to 9 independent 16-byte loads per lane (C % 4 == 0) so that its L2 latency is paid once
+  // per row, not once per element.
+  const int nq = C >> 2;                 // float4 per row
+  for (int j = warp; j < SQ; j += 8) {
+    const float4* wrow = reinterpret_cast<const float4*>(wr + (size_t)j * C);
+    float a[kSeImgs];
+#pragma unroll
+    for (int g = 0; g < kSeImgs; ++g) a[g] = 0.f;
+    constexpr int kB2 = 9;               // 9 x 32 lanes x 4 = 1152 channels per batch: one L2 round trip per row
+    for (int q0 = lane; q0 < nq; q0 += 32 * kB2) {
+      float4 w4[kB2];
+#pragma unroll
+      for (int u = 0; u < kB2; ++u) w4[u] = (q0 + 32 * u < nq) ? wrow[q0 + 32 * u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kB2; ++u) {
+        if (q0 + 32 * u < nq) {
+#pragma unroll
+          for (int g = 0; g < kSeImgs; ++g) {
+            const float4 m = *reinterpret_cast<const float4*>(mean + g * C + 4 * (q0 + 32 * u));
+            a[g] = fmaf(w4[u].x, m.x, fmaf(w4[u].y, m.y, fmaf(w4[u].z, m.z, fmaf(w4[u].w, m.w, a[g]))));
+          }
+        }
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    for (int g = 0; g < kSeImgs; ++g) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[g] += __shfl_xor_sync(0xffffffffu, a[g], o);
     }
     if (lane == 0) {
-      part[warp * SQ + j0] = a0;
-      if (j0 + 1 < SQ) part[warp * SQ + j0 + 1] = a1;
-      if (j0 + 2 < SQ) part[warp * SQ + j0 + 2] = a2;
-      if (j0 + 3 < SQ) part[warp * SQ + j0 + 3] = a3;
-    }
-  }
-  __syncthreads();
-  if (tid < SQ) {
-    float s = br[tid];
+      const float b = br[j];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += part[w * SQ + tid];
-    sq[tid] = silu<true>(s);
+      for (int g = 0; g < kSeImgs; ++g) sq[g * SQ + j] = silu<true>(a[g] + b);
+    }
   }
   __syncthreads();
-  // phase 3: gate[c] = sigmoid(be[c] + sum_j we_t[j][c] * s[j])
-  for (int c = tid; c < C; c += 256) {
-    float s0 = be[c], s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int j = 0;
-    for (; j + 4 <= SQ; j += 4) {
-      const float* wp = we_t + (size_t)j * C + c;
-      s0 = fmaf(wp[0], sq[j], s0);
-      s1 = fmaf(wp[C], sq[j + 1], s1);
-      s2 = fmaf(wp[2 * (size_t)C], sq[j + 2], s2);
-      s3 = fmaf(wp[3 * (size_t)C], sq[j + 3], s3);
+  // phase 3: gate[g][c] = sigmoid(be[c] + sum_j we_t[j][c] * s[g][j]); a thread owns 4 consecutive channels
+  // and walks the SQ rows in batches of 12 independent 16-byte loads
+  for (int q = tid; q < nq; q += 256) {
+    const float4 b4 = *reinterpret_cast<const float4*>(be + 4 * q);
+    float4 a[kSeImgs];
+#pragma unroll
+    for (int g = 0; g < kSeImgs; ++g) a[g] = b4;
+    constexpr int kB3 = 12;
+    for (int j0 = 0; j0 < SQ; j0 += kB3) {
+      float4 w4[kB3];
+#pragma unroll
+      for (int u = 0; u < kB3; ++u)
+        w4[u] = (j0 + u < SQ) ? *reinterpret_cast<const float4*>(we_t + (size_t)(j0 + u) * C + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kB3; ++u) {
+        if (j0 + u < SQ) {
+#pragma unroll
+          for (int g = 0; g < kSeImgs; ++g) {
+            const float sv = sq[g * SQ + j0 + u];
+            a[g].x = fmaf(w4[u].x, sv, a[g].x); a[g].y = fmaf(w4[u].y, sv, a[g].y);
+            a[g].z = fmaf(w4[u].z, sv, a[g].z); a[g].w = fmaf(w4[u].w, sv, a[g].w);
+          }
+        }
+      }
     }
-    for (; j < SQ; ++j) s0 = fmaf(we_t[(size_t)j * C + c], sq[j], s0);
-    gate[(size_t)img * C + c] = sigmoidf_<true>((s0 + s1) + (s2 + s3));
+#pragma unroll
+    for (int g = 0; g < kSeImgs; ++g)
+      if (g < n_here)
+        *reinterpret_cast<float4*>(gate + (size_t)(img0 + g) * C + 4 * q) =
+            make_float4(sigmoidf_<true>(a[g].x), sigmoidf_<true>(a[g].y), sigmoidf_<true>(a[g].z), sigmoidf_<true>(a[g].w));
   }
 }
 
@@ -372,6 +528,15 @@ int launch_stem_t(const void* x, const float* w, const float* shift, void* out, 
   const int grid = (int)((total + 127) / 128);
   ProfScope prof(st, 2.0 * 27 * 32 * (double)n_img * Ho * Wo,
                  (double)n_img * ((double)H * W * 3 * sizeof(TIN) + (double)Ho * Wo * 32 * sizeof(T)), "stem");
+  if constexpr (sizeof(T) == 2) {
+    if (W % 16 == 0 && H % 2 == 0 && W * 3 + 10 <= kStemRS && n_img <= 65535) {
+      dim3 grid((Ho + kStemTH - 1) / kStemTH, n_img);
+      stem_tc_kernel<TIN><<<grid, 256, 0, st>>>(reinterpret_cast<const TIN*>(x), w, shift, reinterpret_cast<bf16*>(out), H, W,
+                                                 Ho, Wo);
+      MT_LAUNCH_CHECK("stem_tc_kernel");
+      return MT_OK;
+    }
+  }
   stem_kernel<T, TIN><<<grid, 128, 0, st>>>(reinterpret_cast<const TIN*>(x), w, shift, reinterpret_cast<T*>(out),
                                             n_img, H, W, Ho, Wo, same_pad_lo(H, 3, 2));
   MT_LAUNCH_CHECK("stem_kernel");
@@ -678,11 +843,18 @@ extern "C" int mt_dwconv_se_fwd(int precision, const void* in, const float* w, c
 extern "C" int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br,
                               const float* we, const float* be, float* gate, int n_img, int c, int sq, void* stream) {
   MT_REQUIRE(pool_part && wr && br && we && be && gate, "se_gate: null pointer");
-  MT_REQUIRE(n_img > 0 && c > 0 && sq > 0 && sq <= 256 && hw > 0 && n_chunks > 0 && (size_t)(c + 9 * sq) * 4 <= 48 * 1024,
+  const size_t se_smem = (size_t)kSeImgs * (c + sq) * 4;
+  MT_REQUIRE(n_img > 0 && c > 0 && c % 4 == 0 && sq > 0 && sq <= 256 && hw > 0 && n_chunks > 0 && se_smem <= 96 * 1024,
              "se_gate: bad shape");
+  static bool se_attr = false;
+  if (!se_attr) {
+    cudaError_t e = cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(se_gate)");
+    se_attr = true;
+  }
   ProfScope prof(reinterpret_cast<cudaStream_t>(stream), 4.0 * n_img * (double)c * sq,
                  (double)n_img * c * 4 * (n_chunks + 1), "se_gate");
-  se_gate_kernel<<<n_img, 256, (size_t)(c + 9 * sq) * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
+  se_gate_kernel<<<(n_img + kSeImgs - 1) / kSeImgs, 256, se_smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       pool_part, n_chunks, 1.0f / (float)hw, wr, br, we, be, gate, n_img, c, sq);
   MT_LAUNCH_CHECK("se_gate_kernel");
   return MT_OK;

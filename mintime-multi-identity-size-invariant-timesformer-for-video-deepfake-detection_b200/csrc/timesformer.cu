@@ -287,12 +287,14 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ x, 
 
 template <typename T>
 int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, int mode, void* out, float* cls_attn,
-                  int B, int f, int n, int heads, cudaStream_t st) {
+                  int B, int f, int n, int heads, float* cls_parts, cudaStream_t st) {
   const int N = 1 + f * n;
   const T* q = reinterpret_cast<const T*>(qkv);
   T* o = reinterpret_cast<T*>(out);
   const size_t smem = (size_t)(N + 64 + 32 + 2048) * sizeof(float);
-  {
+  // bf16 path with a tensor-core grouped kernel: the CLS row is computed inside it (partials) + cls_combine_kernel
+  const bool fused_cls = std::is_same<T, bf16>::value && cls_parts != nullptr && (mode == MT_ATTN_SPACE || f <= 32);
+  if (!fused_cls) {
     ProfScope prof(st, 4.0 * B * heads * 64.0 * N, (double)B * N * heads * 64 * 2 * sizeof(T), "attn_cls");
     attn_cls_kernel<T><<<B * heads, 256, smem, st>>>(q, mask, o, cls_attn, N, f, n, heads);
     MT_LAUNCH_CHECK("attn_cls_kernel");
@@ -302,10 +304,15 @@ int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, i
                  mode == MT_ATTN_TIME ? "attn_time" : "attn_space");
   if constexpr (std::is_same<T, bf16>::value) {
     // bf16 path: warp-level tensor-core kernels (attention_mma.cuh)
-    if (mode == MT_ATTN_SPACE) {
-      attn::attn_space_mma_kernel<<<B * heads * f, 128, 0, st>>>(q, o, f, n, heads);
-      MT_LAUNCH_CHECK("attn_space_mma_kernel");
+    auto combine = [&]() -> int {
+      attn::cls_combine_kernel<<<B * heads, 64, 0, st>>>(q, cls_parts, o, cls_attn, N, mode == MT_ATTN_SPACE ? f : n, heads);
+      MT_LAUNCH_CHECK("cls_combine_kernel");
       return MT_OK;
+    };
+    if (fused_cls && mode == MT_ATTN_SPACE) {
+      attn::attn_space_mma_kernel<<<B * heads * f, 160, 0, st>>>(q, mask, o, cls_parts, cls_attn, f, n, heads);
+      MT_LAUNCH_CHECK("attn_space_mma_kernel");
+      return combine();
     }
     const int grid = B * heads * ((n + 3) / 4);
     auto launch_time = [&](auto kern, int nkt, int mt_) -> int {
@@ -314,15 +321,17 @@ int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, i
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(attn_time)");
       }
-      kern<<<grid, 128, dyn, st>>>(q, mask, idmask, o, f, n, heads);
+      kern<<<grid, 256, dyn, st>>>(q, mask, idmask, o, cls_parts, cls_attn, f, n, heads);
       MT_LAUNCH_CHECK("attn_time_mma_kernel");
-      return MT_OK;
+      return combine();
     };
-    if (f <= 15) return launch_time(attn::attn_time_mma_kernel<1, 1>, 1, 1);
-    if (f == 16) return launch_time(attn::attn_time_mma_kernel<2, 1>, 2, 1);
-    if (f <= 31) return launch_time(attn::attn_time_mma_kernel<2, 2>, 2, 2);
-    if (f == 32) return launch_time(attn::attn_time_mma_kernel<3, 2>, 3, 2);
-    // other frame counts: generic kernel below
+    if (fused_cls && mode == MT_ATTN_TIME) {
+      if (f <= 15) return launch_time(attn::attn_time_mma_kernel<1, 1>, 1, 1);
+      if (f == 16) return launch_time(attn::attn_time_mma_kernel<2, 1>, 2, 1);
+      if (f <= 31) return launch_time(attn::attn_time_mma_kernel<2, 2>, 2, 2);
+      return launch_time(attn::attn_time_mma_kernel<3, 2>, 3, 2);
+    }
+    // (no workspace / other frame counts: generic kernel below, CLS row already done by attn_cls_kernel)
   }
   if (mode == MT_ATTN_TIME)
     attn_group_kernel<T, MT_ATTN_TIME><<<B * heads * n, 128, 0, st>>>(q, mask, idmask, o, f, n, heads);
@@ -334,7 +343,11 @@ int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, i
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct TsfWs { size_t x, xn, qkv, o, h, total; };
+size_t attn_ws_bytes(int B, int f, int n, int heads) {
+  return (size_t)B * heads * (size_t)std::max(f, n) * attn::kClsStride * sizeof(float);
+}
+
+struct TsfWs { size_t x, xn, qkv, o, h, cls, total; };
 TsfWs tsf_ws_layout(const mt_tsf_cfg_t& c, int B, int precision) {
   const size_t es = precision == MT_PREC_FP32 ? 4 : 2;
   const size_t rows = (size_t)B * (1 + (size_t)c.num_frames * c.num_patches);
@@ -346,6 +359,7 @@ TsfWs tsf_ws_layout(const mt_tsf_cfg_t& c, int B, int precision) {
   l.qkv = off; off += align_up(rows * 3 * inner * es, 1024);
   l.o = off;   off += align_up(rows * inner * es, 1024);
   l.h = off;   off += align_up(rows * 4 * c.dim * es, 1024);
+  l.cls = off; off += align_up(attn_ws_bytes(B, c.num_frames, c.num_patches, c.heads), 1024);
   l.total = off;
   return l;
 }
@@ -385,9 +399,14 @@ extern "C" int mt_layernorm_fwd(int precision, const float* x, const float* gamm
   return MT_OK;
 }
 
+extern "C" size_t mt_divided_attn_workspace_bytes(int batch, int f, int n, int heads) {
+  if (batch <= 0 || f <= 0 || n <= 0 || heads <= 0) return 0;
+  return attn_ws_bytes(batch, f, n, heads);
+}
+
 extern "C" int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t* mask, const uint8_t* identities_mask,
                                    int mode, void* out, float* cls_attn, int batch, int f, int n, int heads,
-                                   int dim_head, void* stream) {
+                                   int dim_head, void* workspace, size_t workspace_bytes, void* stream) {
   MT_REQUIRE(qkv && mask && out, "divided_attn: null pointer");
   MT_REQUIRE(mode == MT_ATTN_TIME || mode == MT_ATTN_SPACE, "divided_attn: unknown mode %d", mode);
   MT_REQUIRE(mode == MT_ATTN_SPACE || identities_mask, "divided_attn: time mode needs identities_mask");
@@ -396,10 +415,16 @@ extern "C" int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t
              batch, f, n);
   MT_REQUIRE((size_t)(1 + f * n + 2144) * 4 <= 48 * 1024, "divided_attn: too many tokens (%d)", 1 + f * n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (workspace && workspace_bytes < attn_ws_bytes(batch, f, n, heads)) {
+    set_error("divided_attn: workspace too small (%zu < %zu)", workspace_bytes, attn_ws_bytes(batch, f, n, heads));
+    return MT_ERR_WORKSPACE;
+  }
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "divided_attn: workspace must be 16-byte aligned");
+  float* parts = reinterpret_cast<float*>(workspace);   // null: CLS row by the stand-alone kernel
   if (precision == MT_PREC_FP32)
-    return launch_attn_t<float>(qkv, mask, identities_mask, mode, out, cls_attn, batch, f, n, heads, st);
+    return launch_attn_t<float>(qkv, mask, identities_mask, mode, out, cls_attn, batch, f, n, heads, parts, st);
   if (precision == MT_PREC_BF16)
-    return launch_attn_t<bf16>(qkv, mask, identities_mask, mode, out, cls_attn, batch, f, n, heads, st);
+    return launch_attn_t<bf16>(qkv, mask, identities_mask, mode, out, cls_attn, batch, f, n, heads, parts, st);
   set_error("divided_attn: unknown precision %d", precision);
   return MT_ERR_ARG;
 }
@@ -492,7 +517,7 @@ extern "C" int mt_tsf_fwd(const mt_tsf_weights_t* w, const mt_tsf_cfg_t* cfg, co
       rc = mt_pointwise_fwd(precision, xn, aw.w_qkv, nullptr, nullptr, 0, nullptr, 0, qkv, rows, 3 * inner, D, stream);
       if (rc) return rc;
       rc = mt_divided_attn_fwd(precision, qkv, mask, identities_mask, mode == 0 ? MT_ATTN_TIME : MT_ATTN_SPACE, o, amap,
-                               batch, f, n, H, cfg->dim_head, stream);
+                               batch, f, n, H, cfg->dim_head, ws + l.cls, l.total - l.cls, stream);
       if (rc) return rc;
       rc = mt_linear_residual_fwd(precision, o, aw.w_out, aw.b_out, x, rows, D, inner, stream);
       if (rc) return rc;

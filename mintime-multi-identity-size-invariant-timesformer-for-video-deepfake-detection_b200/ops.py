@@ -90,11 +90,14 @@ def divided_attention(qkv, mask_u8, idmask_u8, mode: str, f: int, n: int, heads:
     _lib.require_device(qkv.device)
     out = torch.empty((B, N, heads * dim_head), dtype=T, device=qkv.device)
     cls = torch.empty((B * heads, N), dtype=torch.float32, device=qkv.device) if want_cls_attn else None
+    lib = _lib.load()
+    ws_bytes = int(lib.mt_divided_attn_workspace_bytes(B, f, n, heads))
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        rc = _lib.load().mt_divided_attn_fwd(_lib.prec_id(precision), qkv.data_ptr(), mask_u8.data_ptr(),
-                                             _lib.ptr(idmask_u8), _lib.ATTN_TIME if mode == "time" else _lib.ATTN_SPACE,
-                                             out.data_ptr(), _lib.ptr(cls), B, f, n, heads, dim_head,
-                                             _lib.stream_ptr())
+        rc = lib.mt_divided_attn_fwd(_lib.prec_id(precision), qkv.data_ptr(), mask_u8.data_ptr(),
+                                     _lib.ptr(idmask_u8), _lib.ATTN_TIME if mode == "time" else _lib.ATTN_SPACE,
+                                     out.data_ptr(), _lib.ptr(cls), B, f, n, heads, dim_head, ws.data_ptr(), ws_bytes,
+                                     _lib.stream_ptr())
     _lib.check(rc, "mt_divided_attn_fwd")
     return out, cls
 

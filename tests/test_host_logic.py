@@ -37,7 +37,7 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"multiple of 128" in lib.mt_last_error()
     rc = lib.mt_pointwise_fwd(1, 8, 8, None, None, 0, None, 0, 8, 4, 12, 16, None)   # N % 8 != 0
     assert rc == -1 and b"multiples of 8" in lib.mt_last_error()
-    rc = lib.mt_divided_attn_fwd(1, 8, 8, 8, 0, 8, None, 1, 16, 49, 8, 32, None)     # dim_head != 64
+    rc = lib.mt_divided_attn_fwd(1, 8, 8, 8, 0, 8, None, 1, 16, 49, 8, 32, None, 0, None)     # dim_head != 64
     assert rc == -1 and b"dim_head" in lib.mt_last_error()
     assert lib.mt_effnet_b0_workspace_bytes(0, 1) == 0
     bf16_ws, fp32_ws = lib.mt_effnet_b0_workspace_bytes(4, 1), lib.mt_effnet_b0_workspace_bytes(4, 0)
