@@ -422,44 +422,54 @@ __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, c
 // Fixed reduction orders: deterministic.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kSeImgs = 4;
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_part, int n_chunks, float inv_hw,
-                                                      const float* __restrict__ wr, const float* __restrict__ br,
-                                                      const float* __restrict__ we_t, const float* __restrict__ be,
-                                                      float* __restrict__ gate, int n_img, int C, int SQ) {
+constexpr int kSeThreads = 512;
+constexpr int kSeRowBatch = 12;          // rows of we_t per phase-3 work item
+__global__ void __launch_bounds__(kSeThreads) se_gate_kernel(const float* __restrict__ pool_part, int n_chunks, float inv_hw,
+                                                             const float* __restrict__ wr, const float* __restrict__ br,
+                                                             const float* __restrict__ we_t, const float* __restrict__ be,
+                                                             float* __restrict__ gate, int n_img, int C, int SQ) {
+  // One block = kSeImgs images, one block per SM at most: the kernel is a chain of L2 round trips, so every
+  // phase issues all the loads a thread needs as one batch of independent requests.
   extern __shared__ __align__(16) float sm[];
   float* mean = sm;                      // [kSeImgs][C]
-  float* sq = sm + kSeImgs * C;          // [kSeImgs][SQ]
+  float* sq = sm + kSeImgs * C;          // [kSeImgs][SQ]  (SQ rounded up to 4)
+  float* part3 = sq + kSeImgs * ((SQ + 3) & ~3);   // [JG][kSeImgs][C] phase-3 partial sums
   const int img0 = blockIdx.x * kSeImgs;
   const int n_here = min(kSeImgs, n_img - img0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kSeImgs * C; i += 256) {
-    const int g = i / C, c = i - g * C;
-    double acc = 0.0;                    // fixed order, double: deterministic and as accurate as the reference's mean
-    if (g < n_here) {
-      const float* pp = pool_part + (size_t)(img0 + g) * n_chunks * C + c;
-      int j = 0;
-      for (; j + 8 <= n_chunks; j += 8) {  // 8 independent loads in flight (the per-tile partials of dwconv_simt)
-        float v[8];
+  constexpr int kWarps = kSeThreads / 32;
+  // ---- phase 1: mean over the output pixels = sum of the per-tile partial sums / hw
+  for (int i0 = tid; i0 < kSeImgs * C; i0 += 4 * kSeThreads) {
+    float v[4][8];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // fixed order, double: deterministic and as accurate as the reference's mean
+    for (int j0 = 0; j0 < n_chunks; j0 += 8) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = pp[(size_t)(j + u) * C];
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSeThreads, g = i / C, c = i - g * C;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += (double)v[u];
+        for (int j = 0; j < 8; ++j)
+          v[u][j] = (i < kSeImgs * C && g < n_here && j0 + j < n_chunks)
+                        ? pool_part[((size_t)(img0 + g) * n_chunks + j0 + j) * C + c] : 0.f;
       }
-      for (; j < n_chunks; ++j) acc += (double)pp[(size_t)j * C];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[u] += (double)v[u][j];
     }
-    mean[i] = (float)(acc * (double)inv_hw);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * kSeThreads < kSeImgs * C) mean[i0 + u * kSeThreads] = (float)(acc[u] * (double)inv_hw);
   }
   __syncthreads();
-  // phase 2: s[g][j] = swish(br[j] + sum_c wr[j][c] * mean[g][c]); one warp per squeeze row j.  The row is
-  // fetched as up to 9 independent 16-byte loads per lane (C % 4 == 0) so that its L2 latency is paid once
-  // per row, not once per element.
+  // ---- phase 2: s[g][j] = swish(br[j] + sum_c wr[j][c] * mean[g][c]); one warp per squeeze row j, the row
+  // fetched as up to 9 independent 16-byte loads per lane (C % 4 == 0): one L2 round trip per row
   const int nq = C >> 2;                 // float4 per row
-  for (int j = warp; j < SQ; j += 8) {
+  for (int j = warp; j < SQ; j += kWarps) {
     const float4* wrow = reinterpret_cast<const float4*>(wr + (size_t)j * C);
     float a[kSeImgs];
 #pragma unroll
     for (int g = 0; g < kSeImgs; ++g) a[g] = 0.f;
-    constexpr int kB2 = 9;               // 9 x 32 lanes x 4 = 1152 channels per batch: one L2 round trip per row
+    constexpr int kB2 = 9;
     for (int q0 = lane; q0 < nq; q0 += 32 * kB2) {
       float4 w4[kB2];
 #pragma unroll
@@ -487,36 +497,42 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
-  // phase 3: gate[g][c] = sigmoid(be[c] + sum_j we_t[j][c] * s[g][j]); a thread owns 4 consecutive channels
-  // and walks the SQ rows in batches of 12 independent 16-byte loads
-  for (int q = tid; q < nq; q += 256) {
-    const float4 b4 = *reinterpret_cast<const float4*>(be + 4 * q);
+  // ---- phase 3: gate[g][c] = sigmoid(be[c] + sum_j we_t[j][c] * s[g][j]).  Work item = (4 channels, 12 rows):
+  // 12 independent 16-byte loads, partial sums to shared memory, then a fixed-order sum over the row groups.
+  const int JG = (SQ + kSeRowBatch - 1) / kSeRowBatch;
+  for (int item = tid; item < nq * JG; item += kSeThreads) {
+    const int jg = item / nq, q = item - jg * nq, j0 = jg * kSeRowBatch;
+    float4 w4[kSeRowBatch];
+#pragma unroll
+    for (int u = 0; u < kSeRowBatch; ++u)
+      w4[u] = (j0 + u < SQ) ? *reinterpret_cast<const float4*>(we_t + (size_t)(j0 + u) * C + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 a[kSeImgs];
 #pragma unroll
-    for (int g = 0; g < kSeImgs; ++g) a[g] = b4;
-    constexpr int kB3 = 12;
-    for (int j0 = 0; j0 < SQ; j0 += kB3) {
-      float4 w4[kB3];
+    for (int g = 0; g < kSeImgs; ++g) a[g] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < kB3; ++u)
-        w4[u] = (j0 + u < SQ) ? *reinterpret_cast<const float4*>(we_t + (size_t)(j0 + u) * C + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < kSeRowBatch; ++u) {
+      if (j0 + u < SQ) {
 #pragma unroll
-      for (int u = 0; u < kB3; ++u) {
-        if (j0 + u < SQ) {
-#pragma unroll
-          for (int g = 0; g < kSeImgs; ++g) {
-            const float sv = sq[g * SQ + j0 + u];
-            a[g].x = fmaf(w4[u].x, sv, a[g].x); a[g].y = fmaf(w4[u].y, sv, a[g].y);
-            a[g].z = fmaf(w4[u].z, sv, a[g].z); a[g].w = fmaf(w4[u].w, sv, a[g].w);
-          }
+        for (int g = 0; g < kSeImgs; ++g) {
+          const float sv = sq[g * SQ + j0 + u];
+          a[g].x = fmaf(w4[u].x, sv, a[g].x); a[g].y = fmaf(w4[u].y, sv, a[g].y);
+          a[g].z = fmaf(w4[u].z, sv, a[g].z); a[g].w = fmaf(w4[u].w, sv, a[g].w);
         }
       }
     }
 #pragma unroll
-    for (int g = 0; g < kSeImgs; ++g)
-      if (g < n_here)
-        *reinterpret_cast<float4*>(gate + (size_t)(img0 + g) * C + 4 * q) =
-            make_float4(sigmoidf_<true>(a[g].x), sigmoidf_<true>(a[g].y), sigmoidf_<true>(a[g].z), sigmoidf_<true>(a[g].w));
+    for (int g = 0; g < kSeImgs; ++g) *reinterpret_cast<float4*>(part3 + ((size_t)jg * kSeImgs + g) * C + 4 * q) = a[g];
+  }
+  __syncthreads();
+  for (int i = tid; i < n_here * nq; i += kSeThreads) {
+    const int g = i / nq, q = i - g * nq;
+    float4 a = *reinterpret_cast<const float4*>(be + 4 * q);
+    for (int jg = 0; jg < JG; ++jg) {
+      const float4 p = *reinterpret_cast<const float4*>(part3 + ((size_t)jg * kSeImgs + g) * C + 4 * q);
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    *reinterpret_cast<float4*>(gate + (size_t)(img0 + g) * C + 4 * q) =
+        make_float4(sigmoidf_<true>(a.x), sigmoidf_<true>(a.y), sigmoidf_<true>(a.z), sigmoidf_<true>(a.w));
   }
 }
 
@@ -843,18 +859,19 @@ extern "C" int mt_dwconv_se_fwd(int precision, const void* in, const float* w, c
 extern "C" int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br,
                               const float* we, const float* be, float* gate, int n_img, int c, int sq, void* stream) {
   MT_REQUIRE(pool_part && wr && br && we && be && gate, "se_gate: null pointer");
-  const size_t se_smem = (size_t)kSeImgs * (c + sq) * 4;
-  MT_REQUIRE(n_img > 0 && c > 0 && c % 4 == 0 && sq > 0 && sq <= 256 && hw > 0 && n_chunks > 0 && se_smem <= 96 * 1024,
+  const int se_jg = (sq + kSeRowBatch - 1) / kSeRowBatch;
+  const size_t se_smem = (size_t)kSeImgs * ((size_t)c + ((sq + 3) & ~3) + (size_t)se_jg * c) * 4;
+  MT_REQUIRE(n_img > 0 && c > 0 && c % 4 == 0 && sq > 0 && sq <= 256 && hw > 0 && n_chunks > 0 && se_smem <= 200 * 1024,
              "se_gate: bad shape");
   static bool se_attr = false;
   if (!se_attr) {
-    cudaError_t e = cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(se_gate)");
     se_attr = true;
   }
   ProfScope prof(reinterpret_cast<cudaStream_t>(stream), 4.0 * n_img * (double)c * sq,
                  (double)n_img * c * 4 * (n_chunks + 1), "se_gate");
-  se_gate_kernel<<<(n_img + kSeImgs - 1) / kSeImgs, 256, se_smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  se_gate_kernel<<<(n_img + kSeImgs - 1) / kSeImgs, kSeThreads, se_smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       pool_part, n_chunks, 1.0f / (float)hw, wr, br, we, be, gate, n_img, c, sq);
   MT_LAUNCH_CHECK("se_gate_kernel");
   return MT_OK;
