@@ -169,6 +169,19 @@ int mt_divided_attn_fwd(int precision, const void* qkv, const uint8_t* mask, con
                         int mode, void* out, float* cls_attn, int batch, int f, int n, int heads, int dim_head,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Front half of MBConvBlock.forward in one kernel, bf16 only (model.py:98-107): 1x1 expand conv + BN + swish ->
+ * depthwise kxk stride s (TF-SAME padding) + BN + swish, plus the squeeze-excite pool partial sums; the expanded
+ * tensor never leaves the SM (tcgen05 contraction into TMEM -> shared memory -> stencil).
+ *   in bf16 NHWC [n_img][h][h][cin]; w_exp bf16 [cexp][cin] (BN scale folded), exp_shift f32 [cexp];
+ *   w_dw f32 [k*k][cexp] tap-major (BN scale folded), dw_shift f32 [cexp];
+ *   out bf16 NHWC [n_img][ho][ho][cexp]; pool_part f32 [n_img][mt_expand_dwconv_chunks(...)][cexp].
+ * mt_expand_dwconv_chunks returns 0 when the shape has no fused schedule (cin > 64, ...): callers then run
+ * mt_pointwise_fwd + mt_dwconv_fwd.  mt_mbconv_fwd / mt_effnet_b0_fwd make that choice themselves. */
+int mt_expand_dwconv_chunks(int h, int cin, int cexp, int k, int s);
+int mt_expand_dwconv_fwd(const void* in, const void* w_exp, const float* exp_shift, const float* w_dw,
+                         const float* dw_shift, void* out, float* pool_part, int n_img, int h, int cin, int cexp, int k,
+                         int s, void* stream);
+
 /* Stem: ZeroPad2d(0,1,0,1) + conv 3x3 s2 (3->32) + BN + swish (utils.py:248-276, model.py:276)
  *   x NHWC [n_img][H][W][3] (f32/u8) -> out T NHWC [n_img][H/2][W/2][32] */
 int mt_stem_fwd(int precision, const void* x, int x_dtype, const float* w, const float* shift, void* out, int n_img,

@@ -21,7 +21,7 @@ EXPORTS = [
     "mt_effnet_b0_workspace_bytes", "mt_effnet_b0_fwd", "mt_tsf_workspace_bytes", "mt_tsf_fwd",
     "mt_pointwise_fwd", "mt_linear_residual_fwd", "mt_linear_geglu_fwd", "mt_patch_embed_fwd",
     "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
-    "mt_dwconv_chunks", "mt_dwconv_se_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
+    "mt_dwconv_chunks", "mt_dwconv_se_fwd", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
     "mt_aggregate_attn_fwd", "mt_prof_enable", "mt_prof_reset", "mt_prof_collect", "mt_prof_launch_count",
 ]
 
@@ -103,6 +103,9 @@ def load() -> C.CDLL:
     lib.mt_stem_fwd.argtypes = [i32, vp, i32, fp, fp, vp, i32, i32, i32, vp]
     lib.mt_dwconv_fwd.argtypes = [i32, vp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_se_gate_fwd.argtypes = [fp, i32, i32, fp, fp, fp, fp, fp, i32, i32, i32, vp]
+    lib.mt_expand_dwconv_chunks.argtypes = [i32, i32, i32, i32, i32]
+    lib.mt_expand_dwconv_chunks.restype = i32
+    lib.mt_expand_dwconv_fwd.argtypes = [vp, vp, fp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_dwconv_chunks.argtypes = [i32, i32, i32, i32, i32, i32]
     lib.mt_dwconv_se_fwd.argtypes = [i32, vp, fp, fp, vp, fp, vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_dwconv_chunks.restype = i32

@@ -200,5 +200,8 @@ __device__ __forceinline__ void epi_geglu8(const EpiParams& p, int row, int col,
 int launch_gemm(int precision, const GemmArgs& g, cudaStream_t stream);
 // 4-D TMA descriptor over a bf16 NHWC tensor: box = 64 channels x box_w x box_h x 1 image, 128-byte swizzle
 int make_tmap_nhwc_bf16(CUtensorMap_st* m, const void* base, int n, int h, int w, int c, int box_w, int box_h);
+int make_tmap_nhwc_bf16_kmajor(CUtensorMap_st* m, const void* base, int n, int h, int w, int c, int box_c, int box_w,
+                               int box_h);
+int make_tmap_weights_kmajor(CUtensorMap_st* m, const void* base, int rows, int cols, int box_rows, int box_cols);
 
 }  // namespace mt

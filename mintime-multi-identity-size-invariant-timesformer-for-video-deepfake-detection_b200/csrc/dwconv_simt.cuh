@@ -155,12 +155,58 @@ __device__ __forceinline__ void dw_patch(const uint8_t* tp, const int pstride, c
   }
 }
 
+// All R x 7 patches of one tile that belong to this thread's (channel pair, slot): stencil, BN shift + swish,
+// bf16 store, and the thread's share of the squeeze-excite pool sum.  `tile` points at the channel pair's word
+// of the tile's first input pixel.
+template <int K, int S>
+__device__ __forceinline__ float2 dw_tile(const uint8_t* tile, const int pstride, const int rstride,
+                                          const float2 (&wv)[K * K], const float2 hsh, bf16* __restrict__ out, int img,
+                                          int oy_t, int ox_t, int oy_end, int ox_end, int Ho, int Wo, int C, int c,
+                                          int slot, int n_strips, int strips_x, int NS) {
+  constexpr int R = dw_simt_rows(K, S), SX = kDwSX;
+  float2 psum = make_float2(0.f, 0.f);
+  for (int strip = slot; strip < n_strips; strip += NS) {
+    const int sy = strip / strips_x, sx = strip - sy * strips_x;
+    const int oy0 = sy * R, ox0 = sx * SX;
+    float2 acc[R][SX];
+    dw_patch<K, S, R>(tile + (oy0 * S) * rstride + (ox0 * S) * pstride, pstride, rstride, wv, acc);
+    // outputs: one bf16x2 word per pixel; whole patches (the common case) take the branch-free path
+    uint8_t* op = reinterpret_cast<uint8_t*>(out + (((size_t)img * Ho + oy_t + oy0) * Wo + ox_t + ox0) * C + c);
+    const size_t cbytes = (size_t)C * 2, rbytes = (size_t)Wo * cbytes;
+    if (oy0 + R <= oy_end && ox0 + SX <= ox_end) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        uint8_t* p = op + r * rbytes;
+#pragma unroll
+        for (int j = 0; j < SX; ++j) {
+          const float2 v = silu2(acc[r][j], hsh);
+          psum = __fadd2_rn(psum, v);
+          *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v.x, v.y);
+          p += cbytes;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int j = 0; j < SX; ++j) {
+          if (oy0 + r < oy_end && ox0 + j < ox_end) {
+            const float2 v = silu2(acc[r][j], hsh);
+            psum = __fadd2_rn(psum, v);
+            *reinterpret_cast<uint32_t*>(op + r * rbytes + j * cbytes) = pack_bf16x2(v.x, v.y);
+          }
+        }
+      }
+    }
+  }
+  return psum;
+}
+
 template <int K, int S, int CWT>   // CWT: channels per chunk at compile time (0 = read g.CW)
 __global__ void __launch_bounds__(256, 2)
 dwconv_simt_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict__ w,
                    const float* __restrict__ shift, bf16* __restrict__ out, float* __restrict__ pool_part, int n_img,
                    int Ho, int Wo, int C, int pad_lo, DwSimtGeom g) {
-  constexpr int R = dw_simt_rows(K, S), SX = kDwSX;
   extern __shared__ __align__(128) uint8_t dsm_raw[];
   uint8_t* ring = dsm_raw + ((128u - (ptx::smem_u32(dsm_raw) & 127u)) & 127u);   // stays a shared-space pointer
   float2* red = reinterpret_cast<float2*>(ring + 2 * g.tile_stride);   // [2][threads]
@@ -210,41 +256,8 @@ dwconv_simt_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
     const uint8_t* tile = ring + (step & 1) * g.tile_stride + cp * 4;
     const int oy_t = ty * g.TH, ox_t = tx * g.TW;
     const int oy_end = min(g.TH, Ho - oy_t), ox_end = min(g.TW, Wo - ox_t);   // valid outputs of this tile
-    float2 psum = make_float2(0.f, 0.f);
-    for (int strip = slot; strip < g.n_strips; strip += g.NS) {
-      const int sy = strip / g.strips_x, sx = strip - sy * g.strips_x;
-      const int oy0 = sy * R, ox0 = sx * SX;
-      float2 acc[R][SX];
-      dw_patch<K, S, R>(tile + (oy0 * S) * rstride + (ox0 * S) * pstride, pstride, rstride, wv, acc);
-      // outputs: one bf16x2 word per pixel; whole patches (the common case) take the branch-free path
-      uint8_t* op = reinterpret_cast<uint8_t*>(out + (((size_t)img * Ho + oy_t + oy0) * Wo + ox_t + ox0) * C + c);
-      const size_t cbytes = (size_t)C * 2, rbytes = (size_t)Wo * cbytes;
-      if (oy0 + R <= oy_end && ox0 + SX <= ox_end) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          uint8_t* p = op + r * rbytes;
-#pragma unroll
-          for (int j = 0; j < SX; ++j) {
-            const float2 v = silu2(acc[r][j], hsh);
-            psum = __fadd2_rn(psum, v);
-            *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v.x, v.y);
-            p += cbytes;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-#pragma unroll
-          for (int j = 0; j < SX; ++j) {
-            if (oy0 + r < oy_end && ox0 + j < ox_end) {
-              const float2 v = silu2(acc[r][j], hsh);
-              psum = __fadd2_rn(psum, v);
-              *reinterpret_cast<uint32_t*>(op + r * rbytes + j * cbytes) = pack_bf16x2(v.x, v.y);
-            }
-          }
-        }
-      }
-    }
+    const float2 psum = dw_tile<K, S>(tile, pstride, rstride, wv, hsh, out, img, oy_t, ox_t, oy_end, ox_end, Ho, Wo, C, c,
+                                      slot, g.n_strips, g.strips_x, g.NS);
     float2* rb = red + (step & 1) * g.threads;
     rb[tid] = psum;
     __syncthreads();                              // tile consumed (ring slot free) + partial sums visible

@@ -3,6 +3,7 @@
 // The 1x1 convolutions run in gemm.cu; this file holds the stencil / reduction kernels
 // (stem 3x3, depthwise kxk + BN + swish + SE squeeze, SE excitation) and the layer schedule.
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -10,6 +11,7 @@
 #include "dwconv_simt.cuh"
 #include "dwconv_tc.cuh"
 #include "dwconv_umma.cuh"
+#include "mbconv_fused.cuh"
 
 namespace mt {
 namespace {
@@ -645,6 +647,7 @@ int launch_dw_simt_ks(const CUtensorMap& tm, const float* w, const float* shift,
   if (!attr_set[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(dwconv_simt)");
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set[slot] = true;
   }
   // persistent blocks, statically scheduled: launch exactly as many as are co-resident (registers included),
@@ -741,6 +744,86 @@ int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, 
   return launch_dw_tc_ks<5, 2>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
 }
 
+// ---- fused expand + depthwise (mbconv_fused.cuh).  Measured on B200 at 512 images (us, fused vs expand GEMM +
+// depthwise kernel): block 1 (16->96, 112^2) 503 vs 616; block 2 (24->144, 56^2) 395 vs 383; block 3 328 vs 304;
+// block 4 (40->240, 28^2) 316 vs 248; block 5 140 vs 118 -- the fused kernel wins where the expand GEMM is at its
+// worst (K = 16: 32-byte operand rows) and loses where the stencil dominates (7 stencil warps per SM against 12-16
+// in the stand-alone kernel).  mt_mbconv_fwd therefore fuses blocks with cin <= 16 by default;
+// MINTIME_B200_FUSE=all fuses every block that has a schedule, MINTIME_B200_FUSE=0 none.
+int fuse_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("MINTIME_B200_FUSE");
+    mode = 1;
+    if (e && e[0] == '0') mode = 0;
+    if (e && !strcmp(e, "all")) mode = 2;
+  }
+  return mode;
+}
+
+bool fused_front_geom(FusedGeom* g, int precision, int h, int cin, int cexp, int k, int s, int n_img) {
+  if (precision != MT_PREC_BF16 || cexp == cin) return false;
+  if ((k != 3 && k != 5) || (s != 1 && s != 2)) return false;
+  return fused_geom(g, h, cin, cexp, k, s, n_img, 148);
+}
+
+// the choice mt_mbconv_fwd makes
+bool fuse_block(FusedGeom* g, int precision, int h, int cin, int cexp, int k, int s, int n_img) {
+  const int mode = fuse_mode();
+  if (mode == 0 || (mode == 1 && cin > 16)) return false;
+  return fused_front_geom(g, precision, h, cin, cexp, k, s, n_img);
+}
+
+template <int K, int S>
+int launch_front_ks(const CUtensorMap& tin, const CUtensorMap& tw, const float* exp_shift, const float* w_dw,
+                    const float* dw_shift, bf16* o, float* pool, int n_img, int H, int C, const FusedGeom& g, cudaStream_t st) {
+  const int Ho = (H + S - 1) / S;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const float*, const float*, const float*, bf16*, float*, int,
+                        int, int, int, int, int, int, FusedGeom);
+  const int slot = g.d.CW == 32 ? 0 : (g.d.CW == 48 ? 1 : 2);
+  static const Kern kerns[3] = {mbconv_front_kernel<K, S, 32>, mbconv_front_kernel<K, S, 48>, mbconv_front_kernel<K, S, 64>};
+  Kern kern = kerns[slot];
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(mbconv_front)");
+    // two ~100 KiB blocks per SM need the maximum shared-memory carve-out (the occupancy query honours it)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set[slot] = true;
+  }
+  const int per_sm = 1;                          // one warp-specialised block per SM (it owns all 512 TMEM columns)
+  const int threads = kFrontDw0 + ((g.d.threads + 31) & ~31);
+  const long long work = (long long)n_img * g.d.tiles;
+  const int workers = (int)std::max(1LL, std::min(work, (long long)(device_sms() * per_sm) / g.d.n_cchunks));
+  dim3 grid(workers, g.d.n_cchunks);
+  if (getenv("MINTIME_B200_DEBUG"))
+    fprintf(stderr, "mbconv_front k%d s%d: grid (%d,%d) x %d thr, smem %zu, per_sm %d, tile %dx%d in %dx%d MB %d CW %d tmem %d\n", K, S,
+            workers, g.d.n_cchunks, g.d.threads, g.smem, per_sm, g.d.TH, g.d.TW, g.d.IH, g.d.IW, g.MB, g.d.CW, g.tmem_cols);
+  kern<<<grid, threads, g.smem, st>>>(tin, tw, exp_shift, w_dw, dw_shift, o, pool, n_img, H, H, Ho, Ho, C,
+                                          same_pad_lo(H, K, S), g);
+  MT_LAUNCH_CHECK("mbconv_front_kernel");
+  return MT_OK;
+}
+
+int launch_front(const void* in, const void* w_exp, const float* exp_shift, const float* w_dw, const float* dw_shift,
+                 void* out, float* pool, int n_img, int H, int cin, int cexp, int k, int s, const FusedGeom& g,
+                 cudaStream_t st) {
+  CUtensorMap tin, tw;
+  int rc = make_tmap_nhwc_bf16_kmajor(&tin, in, n_img, H, H, cin, g.kbox, g.d.IW, g.d.IH);
+  if (rc) return rc;
+  rc = make_tmap_weights_kmajor(&tw, w_exp, cexp, cin, g.d.CW, g.kbox);
+  if (rc) return rc;
+  const int Ho = (H + s - 1) / s;
+  ProfScope prof(st, 2.0 * (double)n_img * H * H * cin * cexp + 2.0 * k * k * (double)n_img * Ho * Ho * cexp,
+                 (double)n_img * ((double)H * H * cin + (double)Ho * Ho * cexp) * 2, "mbconv_front k%d s%d C%d->%d H%d", k, s,
+                 cin, cexp, H);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if (k == 3 && s == 1) return launch_front_ks<3, 1>(tin, tw, exp_shift, w_dw, dw_shift, o, pool, n_img, H, cexp, g, st);
+  if (k == 3 && s == 2) return launch_front_ks<3, 2>(tin, tw, exp_shift, w_dw, dw_shift, o, pool, n_img, H, cexp, g, st);
+  if (k == 5 && s == 1) return launch_front_ks<5, 1>(tin, tw, exp_shift, w_dw, dw_shift, o, pool, n_img, H, cexp, g, st);
+  return launch_front_ks<5, 2>(tin, tw, exp_shift, w_dw, dw_shift, o, pool, n_img, H, cexp, g, st);
+}
+
 int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
   // tensor-core kernels: a block sees every tile of an image -> one sum per (image, channel)
   if (precision == MT_PREC_BF16 && dw_simt_ok(h, w_, c, k, s, nullptr)) {
@@ -781,7 +864,10 @@ BlockWs block_ws_layout(const mt_mbconv_spec_t& b, int n_img, int precision) {
   size_t off = 0;
   l.exp = off;  off += b.expand != 1 ? align_up((size_t)b.hw_in * b.hw_in * cexp * n_img * es, 1024) : 0;
   l.dw = off;   off += align_up(ho * ho * cexp * n_img * es, 1024);
-  l.pool = off; off += align_up((size_t)dw_chunks(precision, b.hw_in, b.hw_in, (int)cexp, b.kernel, b.stride) * cexp * n_img * 4, 1024);
+  size_t chunks = (size_t)dw_chunks(precision, b.hw_in, b.hw_in, (int)cexp, b.kernel, b.stride);
+  FusedGeom fg;
+  if (fuse_block(&fg, precision, b.hw_in, b.cin, (int)cexp, b.kernel, b.stride, n_img)) chunks = std::max(chunks, (size_t)fg.d.tiles);
+  l.pool = off; off += align_up(chunks * cexp * n_img * 4, 1024);
   l.gate = off; off += align_up(cexp * n_img * 4, 1024);
   l.counters = off; off += align_up((size_t)n_img * 4, 1024);
   l.total = off;
@@ -856,6 +942,26 @@ extern "C" int mt_dwconv_se_fwd(int precision, const void* in, const float* w, c
                          reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mt_expand_dwconv_chunks(int h, int cin, int cexp, int k, int s) {
+  FusedGeom g;
+  if (h <= 0 || !fused_front_geom(&g, MT_PREC_BF16, h, cin, cexp, k, s, 1)) return 0;
+  return g.d.tiles;
+}
+
+extern "C" int mt_expand_dwconv_fwd(const void* in, const void* w_exp, const float* exp_shift, const float* w_dw,
+                                    const float* dw_shift, void* out, float* pool_part, int n_img, int h, int cin,
+                                    int cexp, int k, int s, void* stream) {
+  MT_REQUIRE(in && w_exp && exp_shift && w_dw && dw_shift && out && pool_part, "expand_dwconv: null pointer");
+  MT_REQUIRE(n_img > 0 && n_img <= 65535 && h > 0, "expand_dwconv: bad shape n=%d h=%d", n_img, h);
+  FusedGeom g;
+  if (!fused_front_geom(&g, MT_PREC_BF16, h, cin, cexp, k, s, n_img)) {
+    set_error("expand_dwconv: no fused schedule for h=%d cin=%d cexp=%d k=%d s=%d", h, cin, cexp, k, s);
+    return MT_ERR_UNSUPPORTED;
+  }
+  return launch_front(in, w_exp, exp_shift, w_dw, dw_shift, out, pool_part, n_img, h, cin, cexp, k, s, g,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br,
                               const float* we, const float* be, float* gate, int n_img, int c, int sq, void* stream) {
   MT_REQUIRE(pool_part && wr && br && we && be && gate, "se_gate: null pointer");
@@ -926,21 +1032,30 @@ extern "C" int mt_mbconv_fwd(int precision, const mt_mbconv_spec_t* spec, const 
   const int sq = std::max(1, b.cin / 4);     // max(1, int(cin * 0.25)), model.py:78
   const void* dw_in = in;
   int rc;
-  if (b.expand != 1) {
+  int chunks = dw_chunks(precision, b.hw_in, b.hw_in, cexp, b.kernel, b.stride);
+  FusedGeom fg;
+  if (b.expand != 1 && fuse_block(&fg, precision, b.hw_in, b.cin, cexp, b.kernel, b.stride, n_img)) {
+    // expand 1x1 + BN + swish + depthwise + BN + swish in one kernel: the expanded tensor stays on chip
     MT_REQUIRE(w->expand.w, "mbconv: expand weights missing");
-    rc = mt_pointwise_fwd(precision, in, w->expand.w, w->expand.shift, nullptr, 0, nullptr, 1, bexp,
-                          n_img * b.hw_in * b.hw_in, cexp, b.cin, stream);
+    rc = launch_front(in, w->expand.w, w->expand.shift, w->dw_w, w->dw_shift, bdw, pool, n_img, b.hw_in, b.cin, cexp,
+                      b.kernel, b.stride, fg, reinterpret_cast<cudaStream_t>(stream));
     if (rc) return rc;
-    dw_in = bexp;
+    chunks = fg.d.tiles;
+  } else {
+    if (b.expand != 1) {
+      MT_REQUIRE(w->expand.w, "mbconv: expand weights missing");
+      rc = mt_pointwise_fwd(precision, in, w->expand.w, w->expand.shift, nullptr, 0, nullptr, 1, bexp,
+                            n_img * b.hw_in * b.hw_in, cexp, b.cin, stream);
+      if (rc) return rc;
+      dw_in = bexp;
+    }
+    // depthwise (+ pool sums) and the SE excitation as two launches: the gate needs the whole image's pool
+    rc = mt_dwconv_fwd(precision, dw_in, w->dw_w, w->dw_shift, bdw, pool, n_img, b.hw_in, b.hw_in, cexp, b.kernel,
+                       b.stride, stream);
+    if (rc) return rc;
   }
-  // depthwise (+ pool sums) and the SE excitation as two launches: the gate needs the whole image's pool, and
-  // one block per image with all 512 images in flight hides the FC latency far better than a fused tail
-  // (mt_dwconv_se_fwd keeps the fused variant; it serialises ~30 us of FC latency per image inside blocks)
-  rc = mt_dwconv_fwd(precision, dw_in, w->dw_w, w->dw_shift, bdw, pool, n_img, b.hw_in, b.hw_in, cexp, b.kernel,
-                     b.stride, stream);
-  if (rc) return rc;
-  rc = mt_se_gate_fwd(pool, dw_chunks(precision, b.hw_in, b.hw_in, cexp, b.kernel, b.stride), ho * ho, w->se_reduce_w,
-                      w->se_reduce_b, w->se_expand_w, w->se_expand_b, gate, n_img, cexp, sq, stream);
+  rc = mt_se_gate_fwd(pool, chunks, ho * ho, w->se_reduce_w, w->se_reduce_b, w->se_expand_w, w->se_expand_b, gate, n_img,
+                      cexp, sq, stream);
   if (rc) return rc;
   const bool skip = b.stride == 1 && b.cin == b.cout;   // model.py:123
   return mt_pointwise_fwd(precision, bdw, w->project.w, w->project.shift, gate, ho * ho, skip ? in : nullptr, 0, out,

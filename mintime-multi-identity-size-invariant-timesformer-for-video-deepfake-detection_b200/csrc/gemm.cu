@@ -631,7 +631,8 @@ int make_tmap_2d(CUtensorMap* m, const void* base, bool f32, int rows, int cols,
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   box_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                   : (box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d pitch=%d box_rows=%d base=%p", (int)r, rows, cols,
@@ -786,6 +787,36 @@ int make_tmap_nhwc_bf16(CUtensorMap_st* m, const void* base, int n, int h, int w
     return MT_ERR_DRIVER;
   }
   return MT_OK;
+}
+
+// 4-D map over a bf16 NHWC tensor whose box rows (box_c channels = 32 / 64 / 128 bytes) are swizzled to match a
+// K-major UMMA operand; channels beyond c are zero-filled
+int make_tmap_nhwc_bf16_kmajor(CUtensorMap_st* m, const void* base, int n, int h, int w, int c, int box_c, int box_w,
+                               int box_h) {
+  auto enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MT_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                            : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d k-major) failed (%d) n=%d h=%d w=%d c=%d box=%dx%dx%d base=%p", (int)r, n, h, w, c,
+              box_c, box_w, box_h, base);
+    return MT_ERR_DRIVER;
+  }
+  return MT_OK;
+}
+
+// 2-D map over bf16 weights [rows][cols], box = box_rows x box_cols (32 / 64 / 128 bytes, matching swizzle)
+int make_tmap_weights_kmajor(CUtensorMap_st* m, const void* base, int rows, int cols, int box_rows, int box_cols) {
+  return make_tmap_2d(m, base, false, rows, cols, cols, box_rows, box_cols * 2);
 }
 
 int make_tmap_nhwc_bf16_plain(CUtensorMap_st* m, const void* base, int n, int h, int w, int c, int box_c, int box_w,

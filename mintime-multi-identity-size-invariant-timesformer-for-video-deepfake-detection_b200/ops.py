@@ -133,6 +133,29 @@ def dwconv(x_nhwc, w_taps, shift, k: int, s: int, precision="bf16"):
     return out, pool
 
 
+def expand_dwconv(x_nhwc, w_exp, exp_shift, w_taps, dw_shift, k: int, s: int):
+    """Fused 1x1 expand + BN + swish + depthwise kxk + BN + swish (bf16).
+    -> (out NHWC bf16, pool_part (n, n_chunks, cexp) float32)"""
+    _prep(x_nhwc, torch.bfloat16); _prep(w_exp, torch.bfloat16)
+    n, h, w, cin = x_nhwc.shape
+    cexp = w_exp.shape[0]
+    assert h == w
+    _lib.require_device(x_nhwc.device)
+    lib = _lib.load()
+    chunks = lib.mt_expand_dwconv_chunks(h, cin, cexp, k, s)
+    if chunks <= 0:
+        raise RuntimeError(f"no fused expand+depthwise schedule for h={h} cin={cin} cexp={cexp} k={k} s={s}")
+    ho = (h + s - 1) // s
+    out = torch.empty((n, ho, ho, cexp), dtype=torch.bfloat16, device=x_nhwc.device)
+    pool = torch.full((n, chunks, cexp), float("nan"), dtype=torch.float32, device=x_nhwc.device)
+    with torch.cuda.device(x_nhwc.device):
+        rc = lib.mt_expand_dwconv_fwd(x_nhwc.data_ptr(), w_exp.data_ptr(), exp_shift.data_ptr(), w_taps.data_ptr(),
+                                      dw_shift.data_ptr(), out.data_ptr(), pool.data_ptr(), n, h, cin, cexp, k, s,
+                                      _lib.stream_ptr())
+    _lib.check(rc, "mt_expand_dwconv_fwd")
+    return out, pool
+
+
 def dwconv_se(x_nhwc, w_taps, shift, k: int, s: int, wr, br, we_t, be, precision="bf16"):
     """Depthwise conv + BN + swish with the SE gate computed by the last block of each image.
     -> (out NHWC, gate (n, c) float32)"""

@@ -246,6 +246,27 @@ def test_dwconv_swish_pool(prec, k, s, h, c):
     assert rel_err(pool.cpu().sum(1), ref.sum((2, 3))) <= tol(prec, 1e-5, 3e-3)
 
 
+@pytest.mark.parametrize("k,s,h,cin,cexp", [(3, 2, 112, 16, 96), (3, 1, 56, 24, 144), (5, 2, 56, 24, 144), (5, 1, 28, 40, 240),
+                                            (3, 2, 28, 40, 240), (3, 1, 14, 8, 32), (5, 1, 21, 64, 128)])
+def test_fused_expand_dwconv(k, s, h, cin, cexp):
+    """expand 1x1 + BN + swish + depthwise + BN + swish in one kernel (tcgen05 -> TMEM -> smem -> stencil) against
+    the two reference convolutions on the same bf16 inputs / bf16-rounded expand weights (model.py:98-107)."""
+    n = 3
+    x = rnd((n, h, h, cin), 1).bfloat16()
+    we = rnd((cexp, cin), 2, cin ** -0.5).bfloat16(); es = rnd((cexp,), 3, 0.3)
+    w = rnd((cexp, 1, k, k), 4, 1.0 / k); ds = rnd((cexp,), 5, 0.3)
+    xr = x.float().permute(0, 3, 1, 2)
+    e = orc.swish(F.conv2d(xr, we.float()[:, :, None, None]) + es[None, :, None, None])
+    e = e.bfloat16().float()                      # the expanded tile is held as bf16 (like the unfused path)
+    ref = orc.swish(F.conv2d(orc.same_pad(e, k, s), w, None, s, 0, 1, cexp) + ds[None, :, None, None])
+    taps = w[:, 0].permute(1, 2, 0).reshape(k * k, cexp).contiguous()
+    out, pool = ops.expand_dwconv(x.to(DEV), we.to(DEV), es.to(DEV), taps.to(DEV), ds.to(DEV), k, s)
+    torch.cuda.synchronize()
+    assert out.shape == (n, (h + s - 1) // s, (h + s - 1) // s, cexp)
+    assert rel_err(out.float().cpu().permute(0, 3, 1, 2), ref) <= 5e-3
+    assert rel_err(pool.cpu().sum(1), ref.sum((2, 3))) <= 4e-3
+
+
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("k,s,h,c,sq", [(3, 2, 112, 96, 4), (5, 1, 14, 672, 28), (5, 2, 56, 144, 6), (3, 1, 7, 1152, 48)])
 def test_dwconv_with_fused_se_gate(prec, k, s, h, c, sq):
