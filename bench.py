@@ -48,6 +48,7 @@ class ClockSampler:
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.index = index
+        self.window = "timed region"
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -55,7 +56,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
+                                          "-i", str(self.index), "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -91,7 +92,8 @@ class ClockSampler:
         # median over the upper half of the samples = clocks under load (the poller also sees idle gaps)
         sm_sorted = sorted(sm)
         load = sm_sorted[len(sm_sorted) // 2:]
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": self.window}
 
 
 def cpu_oracle_videos_per_sec(batch: int, frames: int, identities, steps: int, warmup: int):
@@ -158,7 +160,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--identities", type=lambda s: [int(x) for x in s.split(",")], default=[1])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-batch", type=int, default=2, help="clips per CPU-baseline step")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attention-maps", action="store_true", help="also return the CLS attention maps (config 5)")
     args = ap.parse_args()
@@ -288,8 +290,16 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = lib.mt_prof_launch_count()
+    t_wall = time.perf_counter()
     ms = timed(step_resident, args.steps, 0)
     launches = lib.mt_prof_launch_count() - launches0
+    if rank == 0 and time.perf_counter() - t_wall < 0.4:
+        # nvidia-smi cannot sample faster than ~20 ms: keep the SAME step running (untimed) until the poller has
+        # seen at least ~0.4 s of load, so the clocks / throttle reasons describe this workload
+        sampler.window = "timed region + untimed continuation of the same step (region shorter than the poller needs)"
+        while time.perf_counter() - t_wall < 0.4:
+            step_resident()
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
 
@@ -306,9 +316,9 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_oracle_videos_per_sec(args.cpu_batch, f, args.identities, 3, 1)
+        v, sec, cores = cpu_oracle_videos_per_sec(args.cpu_batch, f, args.identities, 5, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_batch} clips x {f} frames per step, 3 timed steps after 1 warm-up "
+               "sample": f"{args.cpu_batch} clips x {f} frames per step, 5 timed steps after 1 warm-up "
                          f"(oracle = fp32 torch-CPU restatement of the reference), {sec:.2f} s/step"}
     if dist is not None:
         dist.barrier()

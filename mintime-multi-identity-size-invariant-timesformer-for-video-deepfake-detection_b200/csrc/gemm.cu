@@ -40,6 +40,7 @@ struct TcParams {
   int tiles_m, tiles_n;
   int tmem_cols;    // power of two >= acc_stages * block_n
   int acc_stages;   // TMEM accumulator buffers (2, or 1 when two CTAs share the SM's 512 columns at block_n > 128)
+  int gate_imgs;    // > 0: SE gate rows of up to this many images are staged in smem per tile (GATED)
   int b_resident;   // 1: the whole weight matrix (one column tile, all k-blocks) is loaded into smem once per block
   const float* gate;
   int rows_per_gate;
@@ -113,6 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 2);   // [N] (8-warp epilogue only)
+  float* gate_s = bias_s + ((p.N + 3) & ~3);                     // [gate_imgs][K] (GATED, when staged)
   constexpr int kEW = epi_warps<KIND, TMA_OUT>();
   constexpr int kGateThread0 = 64 + 32 * kEW;
 
@@ -442,55 +444,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================================================== SE-gate warps (4 warps)
     // Multiply the freshly landed A tile by gate[image(row)][k] in shared memory (reference
     // model.py:115: x = sigmoid(se) * x, ahead of the project conv), then hand it to the MMA warp.
+    // The gate rows of the (at most gate_imgs) images a 128-row tile touches are staged in shared memory once
+    // per tile with coalesced loads, so the TMA -> gate -> MMA critical path holds no global-memory latency.
     const int r = threadIdx.x - kGateThread0;  // tile row 0..127
     PipeState ps;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * kBlockM;
       const int row = m0 + r;
-      const float* grow = p.gate + (size_t)((row < p.M ? row : p.M - 1) / p.rows_per_gate) * p.K;
+      const int img = (row < p.M ? row : p.M - 1) / p.rows_per_gate;
+      const float* grow = p.gate + (size_t)img * p.K;   // global row (fallback when the gates are not staged)
+      const float* gsm = nullptr;
+      if (p.gate_imgs > 0) {
+        const int img0 = m0 / p.rows_per_gate;
+        const int img1 = min(m0 + kBlockM - 1, p.M - 1) / p.rows_per_gate;
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // everyone is done with the previous tile's gates
+        const float4* src = reinterpret_cast<const float4*>(p.gate + (size_t)img0 * p.K);
+        const int n4 = (img1 - img0 + 1) * (p.K >> 2);
+        for (int i = r; i < n4; i += 128) reinterpret_cast<float4*>(gate_s)[i] = src[i];
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        gsm = gate_s + (size_t)(img - img0) * p.K;
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
-        // the gate values do not depend on the tile: fetch them BEFORE waiting for the TMA so their L2
-        // latency overlaps the load instead of sitting on the TMA -> gate -> MMA critical path
-        // (first half of the row's gates only: registers are shared with 8 epilogue warps at 2 blocks per SM)
-        float4 gv[8];
+        const float* gk = (gsm ? gsm : grow) + kb * kBlockK;
+        // gates not staged (single k-block shapes): fetch the first half of the row's gates BEFORE waiting for the
+        // TMA so that their L2 latency overlaps the load
+        float4 pre[8];
+        if (!gsm) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int k = kb * kBlockK + c * 8;
-          if (k < p.K) {
-            gv[2 * c] = *reinterpret_cast<const float4*>(grow + k);
-            gv[2 * c + 1] = *reinterpret_cast<const float4*>(grow + k + 4);
-          }
+          for (int c = 0; c < 4; ++c)
+            if (kb * kBlockK + c * 8 < p.K) {
+              pre[2 * c] = *reinterpret_cast<const float4*>(gk + c * 8);
+              pre[2 * c + 1] = *reinterpret_cast<const float4*>(gk + c * 8 + 4);
+            }
         }
         ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
         uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          if (hb == 1) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int k = kb * kBlockK + 32 + c * 8;
-              if (k < p.K) {
-                gv[2 * c] = *reinterpret_cast<const float4*>(grow + k);
-                gv[2 * c + 1] = *reinterpret_cast<const float4*>(grow + k + 4);
-              }
-            }
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int c = hb * 4 + c4;
-            const int k = kb * kBlockK + c * 8;
-            if (k < p.K) {
-              uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
-              uint4 u = *ptr;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-              const float4 g0 = gv[2 * c4], g1 = gv[2 * c4 + 1];
-              float2 f;
-              f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
-              f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
-              f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
-              f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
-              *ptr = u;
-            }
+        for (int c = 0; c < 8; ++c) {
+          const int k = kb * kBlockK + c * 8;
+          if (k < p.K) {
+            const bool use_pre = !gsm && c < 4;
+            const float4 g0 = use_pre ? pre[2 * (c & 3)] : *reinterpret_cast<const float4*>(gk + c * 8);
+            const float4 g1 = use_pre ? pre[2 * (c & 3) + 1] : *reinterpret_cast<const float4*>(gk + c * 8 + 4);
+            uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
+            uint4 u = *ptr;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            float2 f;
+            f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
+            f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
+            f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
+            f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
+            *ptr = u;
           }
         }
         ptx::fence_proxy_async_smem();
@@ -678,8 +682,15 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   p.b_resident = (p.tiles_n == 1 && num_kb * b_block <= 40 * 1024) ? 1 : 0;
   const int stage_bytes = kAStageBytes + (p.b_resident ? 0 : b_block);
   const int bias_bytes = kEW == 8 ? ((g.N * 4 + 15) & ~15) : 0;
+  // SE gates staged per tile: a 128-row tile touches at most (127 / rows_per_gate) + 2 images
+  p.gate_imgs = 0;
+  int gate_bytes = 0;
+  if (GATED && kEW == 8 && g.K % 4 == 0 && num_kb >= 2) {
+    const int imgs = (kBlockM - 1) / g.rows_per_gate + 2;
+    if (imgs * g.K * 4 <= 20 * 1024) { p.gate_imgs = imgs; gate_bytes = imgs * g.K * 4; }
+  }
   const int fixed = (TMA_OUT ? 2 * kStagingBytes : 0) + 1024 /*align slack*/ + (3 * kMaxStages + 5) * 8 + 16 + bias_bytes +
-                    (p.b_resident ? num_kb * b_block : 0);
+                    gate_bytes + (p.b_resident ? num_kb * b_block : 0);
   // two blocks per SM (2 x (112 KiB + 1 KiB reserved) <= 228 KiB, 2 x 256 TMEM columns) whenever the tile is at
   // most 128 wide, and for the 8-warp epilogue also up to 256 wide when K fits one k-block: the accumulator is
   // then single buffered and the other block's epilogue covers the MMA latency
