@@ -792,13 +792,13 @@ int launch_front_ks(const CUtensorMap& tin, const CUtensorMap& tw, const float* 
     attr_set[slot] = true;
   }
   const int per_sm = 1;                          // one warp-specialised block per SM (it owns all 512 TMEM columns)
-  const int threads = kFrontDw0 + ((g.d.threads + 31) & ~31);
+  const int threads = 32 + 32 * g.nd + ((g.d.threads + 31) & ~31);
   const long long work = (long long)n_img * g.d.tiles;
   const int workers = (int)std::max(1LL, std::min(work, (long long)(device_sms() * per_sm) / g.d.n_cchunks));
   dim3 grid(workers, g.d.n_cchunks);
   if (getenv("MINTIME_B200_DEBUG"))
-    fprintf(stderr, "mbconv_front k%d s%d: grid (%d,%d) x %d thr, smem %zu, per_sm %d, tile %dx%d in %dx%d MB %d CW %d tmem %d\n", K, S,
-            workers, g.d.n_cchunks, g.d.threads, g.smem, per_sm, g.d.TH, g.d.TW, g.d.IH, g.d.IW, g.MB, g.d.CW, g.tmem_cols);
+    fprintf(stderr, "mbconv_front k%d s%d: grid (%d,%d) x %d thr (%d drain warps, %d stencil thr), smem %zu, tile %dx%d in %dx%d MB %d CW %d tmem %d\n",
+            K, S, workers, g.d.n_cchunks, threads, g.nd, g.d.threads, g.smem, g.d.TH, g.d.TW, g.d.IH, g.d.IW, g.MB, g.d.CW, g.tmem_cols);
   kern<<<grid, threads, g.smem, st>>>(tin, tw, exp_shift, w_dw, dw_shift, o, pool, n_img, H, H, Ho, Ho, C,
                                           same_pad_lo(H, K, S), g);
   MT_LAUNCH_CHECK("mbconv_front_kernel");

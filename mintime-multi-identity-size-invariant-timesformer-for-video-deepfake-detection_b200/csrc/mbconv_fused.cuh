@@ -30,6 +30,7 @@ struct FusedGeom {
   int w_stride;            // bytes of the weight slice (CW * row_bytes, 1024-aligned)
   int pitch, exp_bytes;    // expanded-tile pixel pitch (CW*2 + 16) and size
   int tmem_cols;
+  int nd;                  // drain warps (4 or 8); the stencil gets the remaining warps of the 512-thread block
   size_t smem;
 };
 
@@ -68,7 +69,11 @@ inline bool fused_geom(FusedGeom* out, int H, int cin, int C, int k, int s, int 
             halo += (double)(std::min(H, y0 + IH) - std::max(0, y0)) * (std::min(W, x0 + IW) - std::max(0, x0));
           }
         halo /= (double)H * W;
-        for (int NS = 1; NS <= 224 / CP; ++NS) {   // <= 7 stencil warps next to the control + 8 drain warps
+        // Warp split: drain-heavy shapes (K = 16: the expanded tile is 6x the input and every element costs a tanh)
+        // get 8 drain warps -- one per SM sub-partition leaves the MUFU pipe half idle (measured 671 -> 503 us on
+        // block 1) -- the others 4 drain + up to 11 stencil warps (block 2: 395 -> 384 us).
+        const int nd = cin <= 16 ? 8 : 4;
+        for (int NS = 1; NS <= (480 - 32 * nd) / CP; ++NS) {
           const int thr = CP * NS;
           if (thr < 128) continue;
           const size_t smem = 1024 + 2 * (size_t)a_stride + w_stride + 2 * (size_t)exp_bytes + 2 * (size_t)((thr + 31) & ~31) * 8 +
@@ -91,6 +96,7 @@ inline bool fused_geom(FusedGeom* out, int H, int cin, int C, int k, int s, int 
             g.kbox = kbox; g.row_bytes = row_bytes; g.ksteps = cdiv(cin, 16);
             g.n_pix = n_pix; g.MB = MB; g.a_stride = a_stride; g.w_stride = w_stride;
             g.pitch = pitch; g.exp_bytes = exp_bytes;
+            g.nd = nd;
             g.smem = smem;
           }
         }
@@ -121,14 +127,13 @@ __device__ __forceinline__ uint64_t umma_smem_desc_rows(uint32_t smem_addr, int 
 
 // Warp roles (one block per SM, mbarrier hand-offs only -- no block-wide barrier in the steady state):
 //   warp 0        (one thread) TMA producer of the input tiles + tcgen05.mma issuer
-//   warps 1-8     drain: TMEM -> BN shift + swish (MUFU) -> padding mask -> bf16 tile in shared memory;
-//                 warp w reads the TMEM lane quadrant w % 4, the two warps of a quadrant alternate 128-pixel
-//                 blocks (two drain warps per SM sub-partition: one alone leaves the MUFU pipe half idle)
-//   warps 5..     stencil: dw_tile on the finished tile (FFMA2), output + pool partial sums
+//   warps 1..nd   drain: TMEM -> BN shift + swish (MUFU) -> padding mask -> bf16 tile in shared memory;
+//                 warp w reads the TMEM lane quadrant w % 4; nd = 8 (the two warps of a quadrant alternate 128-pixel
+//                 blocks) for drain-heavy shapes -- one drain warp per SM sub-partition leaves the MUFU pipe half
+//                 idle -- nd = 4 for stencil-heavy ones (fused_geom's cost model decides)
+//   warps nd+1..  stencil: dw_tile on the finished tile (FFMA2), output + pool partial sums
 // Input tiles, TMEM accumulators and expanded tiles are all double buffered, so the MUFU-bound drain of tile
 // i+1 overlaps the FMA-bound stencil of tile i on the same SM.
-constexpr int kFrontDrainWarps = 8;
-constexpr int kFrontDw0 = 32 + 32 * kFrontDrainWarps;   // first stencil thread
 
 template <int K, int S, int CW>
 __global__ void __launch_bounds__(512, 1)
@@ -142,6 +147,8 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   uint8_t* a_buf = sm;                                   // [2][a_stride]   input tiles (UMMA A operand)
   uint8_t* w_buf = a_buf + 2 * g.a_stride;               // [CW][row_bytes] expand weights (UMMA B operand)
   uint8_t* exp_buf = w_buf + g.w_stride;                 // [2][exp_bytes]  expanded activations, bf16, pitch PSTRIDE
+  const int nd = g.nd;                                   // drain warps 1..nd
+  const int dw0 = 32 + 32 * nd;                          // first stencil thread
   const int n_dw = g.d.threads;                          // CP * NS stencil threads (the launch rounds up to a warp)
   const int n_dw_pad = (n_dw + 31) & ~31;
   float2* red = reinterpret_cast<float2*>(exp_buf + 2 * g.exp_bytes);   // [2][n_dw_pad]
@@ -171,8 +178,8 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       ptx::mbar_init(&a_full[i], 1);
       ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&t_full[i], 1);
-      ptx::mbar_init(&t_empty[i], kFrontDrainWarps);     // one arrival per drain warp
-      ptx::mbar_init(&e_full[i], kFrontDrainWarps);
+      ptx::mbar_init(&t_empty[i], (uint32_t)nd);         // one arrival per drain warp
+      ptx::mbar_init(&e_full[i], (uint32_t)nd);
       ptx::mbar_init(&e_empty[i], (uint32_t)(n_dw_pad >> 5));   // one arrival per stencil warp
     }
     ptx::mbar_init(&bar_w, 1);
@@ -230,7 +237,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       }
     }
     __syncwarp();
-  } else if (warp <= kFrontDrainWarps) {
+  } else if (warp <= nd) {
     // ===================================================================== drain warps (TMEM -> swish -> smem)
     const int quad = warp & 3, half = (warp - 1) >> 2;
     for (int step = 0; step < my_steps; ++step) {
@@ -242,7 +249,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       ptx::mbar_wait(&t_full[s], ph);
       ptx::tc_fence_after();
       uint8_t* exp_tile = exp_buf + s * g.exp_bytes;
-      for (int mb = half; mb < g.MB; mb += kFrontDrainWarps / 4) {
+      for (int mb = half; mb < g.MB; mb += nd >> 2) {
         const int row = mb * 128 + quad * 32 + lane;     // pixel of the input tile
         const int iy = row / IW, ix = row - iy * IW;
         const int gy = y0 + iy, gx = x0 + ix;
@@ -253,7 +260,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
 #pragma unroll
         for (int c16 = 0; c16 < CW / 16; ++c16) ptx::tmem_ld_32x32b_x16(taddr + c16 * 16, r[c16]);
         ptx::tmem_ld_wait();
-        if (mb + kFrontDrainWarps / 4 >= g.MB) {         // this warp's last TMEM read of the tile: hand it back
+        if (mb + (nd >> 2) >= g.MB) {                    // this warp's last TMEM read of the tile: hand it back
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&t_empty[s]);
@@ -287,7 +294,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     }
   } else {
     // ===================================================================== stencil warps
-    const int dtid = tid - kFrontDw0;
+    const int dtid = tid - dw0;
     const bool active = dtid < n_dw;
     const int cp = active ? dtid % CP : 0, slot = active ? dtid / CP : 0;
     const int c = cbase + 2 * cp;
