@@ -182,6 +182,17 @@ int mt_expand_dwconv_fwd(const void* in, const void* w_exp, const float* exp_shi
                          const float* dw_shift, void* out, float* pool_part, int n_img, int h, int cin, int cexp, int k,
                          int s, void* stream);
 
+/* Clip metadata assembled on the device instead of in DeepFakesDataset.__getitem__ (deepfakes_dataset.py:259-330) /
+ * predict.py generate_masks (:254-352), from the per-identity slot table of each clip:
+ *   slots, n_real i32 [batch][max_identities]: face slots owned by each identity (sum <= f) and how many hold a face;
+ *   frame_no, ratio i32 [batch][f]: source frame number and int(face_area*100/video_area) of the face in each slot
+ *   identity_attention: 0 -> every slot is valid (deepfakes_dataset.py:285-286)
+ * -> mask u8 [batch][f], identities_mask u8 [batch][f][f], size_embedding i32 [batch][f] (0 = padding, 1..20 = size
+ *    bucket), positions i64 [batch][1 + f*n_patches] -- the tensors mt_tsf_fwd / the forward of the model take. */
+int mt_clip_meta_fwd(const int32_t* slots, const int32_t* n_real, const int32_t* frame_no, const int32_t* ratio,
+                     int max_identities, int identity_attention, uint8_t* mask, uint8_t* identities_mask,
+                     int32_t* size_embedding, int64_t* positions, int batch, int f, int n_patches, void* stream);
+
 /* Stem: ZeroPad2d(0,1,0,1) + conv 3x3 s2 (3->32) + BN + swish (utils.py:248-276, model.py:276)
  *   x NHWC [n_img][H][W][3] (f32/u8) -> out T NHWC [n_img][H/2][W/2][32] */
 int mt_stem_fwd(int precision, const void* x, int x_dtype, const float* w, const float* shift, void* out, int n_img,

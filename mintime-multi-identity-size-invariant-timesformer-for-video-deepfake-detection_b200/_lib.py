@@ -22,7 +22,7 @@ EXPORTS = [
     "mt_pointwise_fwd", "mt_linear_residual_fwd", "mt_linear_geglu_fwd", "mt_patch_embed_fwd",
     "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
     "mt_dwconv_chunks", "mt_dwconv_se_fwd", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
-    "mt_aggregate_attn_fwd", "mt_prof_enable", "mt_prof_reset", "mt_prof_collect", "mt_prof_launch_count",
+    "mt_aggregate_attn_fwd", "mt_clip_meta_fwd", "mt_prof_enable", "mt_prof_reset", "mt_prof_collect", "mt_prof_launch_count",
 ]
 
 vp, fp, i32, sz = C.c_void_p, C.c_void_p, C.c_int, C.c_size_t   # all device pointers travel as void*
@@ -116,6 +116,7 @@ def load() -> C.CDLL:
     lib.mt_mbconv_fwd.argtypes = [i32, C.POINTER(MBConvSpec), C.POINTER(MBConv), vp, vp, i32, vp, sz, vp]
     lib.mt_head_fwd.argtypes = [fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, vp]
     lib.mt_aggregate_attn_fwd.argtypes = [fp, fp, fp, i32, i32, i32, i32, C.c_float, vp]
+    lib.mt_clip_meta_fwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.mt_prof_enable.argtypes = [i32]
     lib.mt_prof_enable.restype = None
     lib.mt_prof_reset.restype = None

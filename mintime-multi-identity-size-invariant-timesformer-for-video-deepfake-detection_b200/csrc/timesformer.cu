@@ -588,3 +588,83 @@ extern "C" int mt_aggregate_attn_fwd(const float* space_attn, const float* time_
   MT_LAUNCH_CHECK("aggregate_attn_kernel");
   return MT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Clip metadata on the device: the mask / identities_mask / size-embedding / temporal
+// position tensors that DeepFakesDataset.__getitem__ (deepfakes_dataset.py:259-330) and predict.py's
+// generate_masks (:254-352) assemble on the host for every clip, from the per-identity slot table:
+//   identity i owns slots[i] consecutive face slots, the first n_real[i] hold faces, the rest are padding
+//   size_embedding = bucket(ratio) in 1..20 for faces (SIZE_EMB_DICT, :30-31 / :259-263: (0..5)->1, (6..10)->2, ...),
+//                    0 for padding (:273-274)
+//   mask           = 1 for faces, 0 for padding when identity attention is on (:281-284), all ones otherwise
+//   padded slots repeat the identity's LAST (max) source frame number (:277), 0 when the identity has no face
+//   identities_mask[q][k] = q and k belong to the same identity (:314-321)
+//   positions      = [0] + for each slot the 49 token positions (p-1)*n+1 .. p*n of p = 1-based rank of the slot's
+//                    frame number among the clip's distinct frame numbers (:323-329)
+// One block per clip, one thread per slot.
+// ---------------------------------------------------------------------------------------------------
+namespace mt {
+namespace {
+__global__ void __launch_bounds__(64) clip_meta_kernel(const int* __restrict__ slots, const int* __restrict__ n_real,
+                                                       const int* __restrict__ frame_no, const int* __restrict__ ratio,
+                                                       int max_ids, int identity_attention, uint8_t* __restrict__ mask,
+                                                       uint8_t* __restrict__ idmask, int* __restrict__ size_emb,
+                                                       long long* __restrict__ positions, int f, int n) {
+  __shared__ int ident[64], frames[64], first[64];
+  const int b = blockIdx.x, j = threadIdx.x;
+  int my_id = -1, start = 0, real = 0, fr = 0;
+  if (j < f) {
+    int s0 = 0;
+    for (int i = 0; i < max_ids; ++i) {
+      const int ns = slots[b * max_ids + i];
+      if (j >= s0 && j < s0 + ns) { my_id = i; start = s0; }
+      s0 += ns;
+    }
+    if (my_id >= 0) {
+      const int nr = n_real[b * max_ids + my_id];
+      real = j - start < nr;
+      if (real) {
+        fr = frame_no[b * f + j];
+      } else {                                   // padding repeats the identity's max frame number (0 if none)
+        for (int k = 0; k < nr; ++k) fr = max(fr, frame_no[b * f + start + k]);
+      }
+    }
+    ident[j] = my_id;
+    frames[j] = fr;
+  }
+  __syncthreads();
+  if (j >= f) return;
+  int is_first = 1;
+  for (int k = 0; k < j; ++k) is_first &= frames[k] != fr;
+  first[j] = is_first;
+  __syncthreads();
+  int rank = 1;                                  // 1-based rank among the distinct frame numbers
+  for (int k = 0; k < f; ++k) rank += first[k] && frames[k] < fr;
+  int bucket = 0;
+  if (real) {
+    const int r = ratio[b * f + j];
+    bucket = r <= 5 ? 1 : min(20, (r + 4) / 5);  // (0..5)->1, (6..10)->2, ..., (96..100)->20; larger ratios clamp to 20
+  }
+  size_emb[b * f + j] = bucket;
+  mask[b * f + j] = (real || !identity_attention) ? 1 : 0;
+  for (int k = 0; k < f; ++k) idmask[((size_t)b * f + j) * f + k] = my_id >= 0 && ident[k] == my_id;
+  long long* pos = positions + (size_t)b * (1 + f * n);
+  if (j == 0) pos[0] = 0;
+  for (int p = 0; p < n; ++p) pos[1 + j * n + p] = (long long)(rank - 1) * n + 1 + p;
+}
+}  // namespace
+}  // namespace mt
+
+extern "C" int mt_clip_meta_fwd(const int32_t* slots, const int32_t* n_real, const int32_t* frame_no, const int32_t* ratio,
+                                int max_identities, int identity_attention, uint8_t* mask, uint8_t* identities_mask,
+                                int32_t* size_embedding, int64_t* positions, int batch, int f, int n_patches, void* stream) {
+  MT_REQUIRE(slots && n_real && frame_no && ratio && mask && identities_mask && size_embedding && positions,
+             "clip_meta: null pointer");
+  MT_REQUIRE(batch > 0 && f >= 1 && f <= 64 && n_patches >= 1 && max_identities >= 1, "clip_meta: bad shape B=%d f=%d n=%d ids=%d",
+             batch, f, n_patches, max_identities);
+  mt::clip_meta_kernel<<<batch, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      slots, n_real, frame_no, ratio, max_identities, identity_attention, mask, identities_mask, size_embedding,
+      reinterpret_cast<long long*>(positions), f, n_patches);
+  MT_LAUNCH_CHECK("clip_meta_kernel");
+  return MT_OK;
+}

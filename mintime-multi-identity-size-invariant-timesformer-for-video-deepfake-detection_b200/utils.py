@@ -52,3 +52,31 @@ def aggregate_attentions(attentions, heads, num_frames, frames_per_identity, sca
             identity_attention = sum(aggregated[-1][previous_identity_frames - 1:identity_frames - 1])
         identity_attentions.append(identity_attention)
     return aggregated, identity_attentions
+
+
+def build_clip_meta(slots: torch.Tensor, n_real: torch.Tensor, frame_no: torch.Tensor, ratio: torch.Tensor,
+                    num_patches: int = 49, identity_attention: bool = True):
+    """mask / identities_mask / size_embedding / positions of a batch of clips, assembled on the device
+    (mt_clip_meta_fwd) from the per-identity slot table -- what ``DeepFakesDataset.__getitem__``
+    (deepfakes_dataset.py:259-330) and predict.py's ``generate_masks`` build per clip on the host.
+
+    slots, n_real: int32 (B, max_identities); frame_no, ratio: int32 (B, f); all on the same CUDA device.
+    Returns a dict with the tensors ``SizeInvariantTimeSformer.forward`` takes: mask bool (B,f), identities_mask
+    bool (B,f,f), size_embedding int32 (B,f), positions int64 (B, 1+f*num_patches)."""
+    dev = slots.device
+    _lib.require_device(dev)
+    for t in (slots, n_real, frame_no, ratio):
+        if t.dtype != torch.int32 or not t.is_contiguous() or t.device != dev:
+            raise ValueError("build_clip_meta takes contiguous int32 tensors on one device")
+    b, ids = slots.shape
+    f = frame_no.shape[1]
+    mask = torch.empty((b, f), dtype=torch.uint8, device=dev)
+    idm = torch.empty((b, f, f), dtype=torch.uint8, device=dev)
+    se = torch.empty((b, f), dtype=torch.int32, device=dev)
+    pos = torch.empty((b, 1 + f * num_patches), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().mt_clip_meta_fwd(slots.data_ptr(), n_real.data_ptr(), frame_no.data_ptr(), ratio.data_ptr(), ids,
+                                          1 if identity_attention else 0, mask.data_ptr(), idm.data_ptr(), se.data_ptr(),
+                                          pos.data_ptr(), b, f, num_patches, _lib.stream_ptr())
+    _lib.check(rc, "mt_clip_meta_fwd")
+    return {"mask": mask.view(torch.bool), "identities_mask": idm.view(torch.bool), "size_embedding": se, "positions": pos}

@@ -467,3 +467,80 @@ def test_full_size_properties_bf16():
     noisy[padded] = torch.randint(0, 256, noisy[padded].shape, device=DEV).float()
     logits_n, _ = _run(ext, model, noisy, meta)
     assert padded.any() and torch.equal(logits_n, logits)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("f,max_ids", [(8, 2), (16, 4), (32, 3), (16, 1)])
+def test_clip_meta_on_device(f, max_ids):
+    """mt_clip_meta_fwd against the line-by-line restatement of deepfakes_dataset.py:259-330 (bit exact): random slot
+    tables with padded identities, identities without any face, repeated frame numbers across identities, ratios on
+    the bucket edges."""
+    from oracle.clip_meta_oracle import clip_meta
+    from mintime_b200.utils import build_clip_meta
+    rng = np.random.default_rng(f * 10 + max_ids)
+    B = 37
+    slots = np.zeros((B, max_ids), np.int32); n_real = np.zeros((B, max_ids), np.int32)
+    frame_no = np.zeros((B, f), np.int32); ratio = np.zeros((B, f), np.int32)
+    want = []
+    for b in range(B):
+        cuts = np.sort(rng.choice(np.arange(1, f), size=max_ids - 1, replace=False)) if max_ids > 1 else np.array([], int)
+        sizes = np.diff(np.concatenate(([0], cuts, [f])))
+        ids, start = [], 0
+        for i, ns in enumerate(sizes):
+            nr = int(rng.integers(0, ns + 1)) if rng.random() < 0.6 else int(ns)
+            fr = np.sort(rng.choice(np.arange(0, 40), size=nr, replace=False)) if nr else np.array([], int)
+            ra = rng.choice([0, 1, 5, 6, 10, 11, 49, 50, 51, 95, 96, 100], size=nr)
+            slots[b, i] = ns; n_real[b, i] = nr
+            frame_no[b, start:start + nr] = fr; ratio[b, start:start + nr] = ra
+            frame_no[b, start + nr:start + ns] = 777          # garbage in padded slots must be ignored
+            ids.append((int(ns), [(int(a), int(c)) for a, c in zip(fr, ra)]))
+            start += ns
+        want.append(clip_meta(ids, f))
+    for ia in (True, False):
+        out = build_clip_meta(torch.from_numpy(slots).to(DEV), torch.from_numpy(n_real).to(DEV),
+                              torch.from_numpy(frame_no).to(DEV), torch.from_numpy(ratio).to(DEV), identity_attention=ia)
+        torch.cuda.synchronize()
+        for b in range(B):
+            se, mask, idm, pos = want[b]
+            assert (out["size_embedding"][b].cpu().numpy() == se).all()
+            assert (out["mask"][b].cpu().numpy() == (mask if ia else np.ones_like(mask))).all()
+            assert (out["identities_mask"][b].cpu().numpy() == idm).all()
+            assert (out["positions"][b].cpu().numpy() == pos).all()
+
+
+@pytest.mark.gpu
+def test_cuda_graph_capture_replays_bit_exact():
+    """The C ABI neither allocates nor synchronises (include/mintime_b200.h), so the whole hot path can be captured
+    in a CUDA graph; a replay on new input data must equal the eager result bit for bit (deterministic kernels)."""
+    cfg, esd, tsd, meta, frames = case_inputs("b2_f16_id2")
+    B, f = frames.shape[:2]
+    ext = EfficientNet.from_name("efficientnet-b0", precision="bf16"); ext.load_state_dict(esd); ext = ext.to(DEV).eval()
+    model = SizeInvariantTimeSformer(config=cfg, require_attention=True, precision="bf16")
+    model.load_state_dict(tsd); model = model.to(DEV).eval()
+    kw = dict(mask=meta["mask"].to(DEV), size_embedding=meta["size_embedding"].to(DEV),
+              identities_mask=meta["identities_mask"].to(DEV), positions=meta["positions"].to(DEV))
+    static_in = frames.to(DEV).clone()
+
+    def fwd():
+        x = static_in.view(B * f, 224, 224, 3).permute(0, 3, 1, 2)
+        feats = ext(x)
+        return model(feats.reshape(B, f, 1280, 7, 7), **kw)
+
+    with torch.no_grad():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fwd()                                     # warm-up: one-time attribute calls, weight packing
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            logits_g, (sa_g, ta_g) = fwd()
+        new = torch.flip(frames, dims=[0]).to(DEV)        # different data through the same graph
+        static_in.copy_(new)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (logits_g.clone(), sa_g.clone(), ta_g.clone())
+        logits_e, (sa_e, ta_e) = fwd()
+        torch.cuda.synchronize()
+    assert torch.equal(got[0], logits_e) and torch.equal(got[1], sa_e) and torch.equal(got[2], ta_e)

@@ -178,3 +178,42 @@ def test_synthetic_clip_metadata_contract():
         assert ((se == 0) == (~m)).all()                                # padded slots carry size 0
         assert im.diagonal(dim1=1, dim2=2).all()
     assert synth.identity_slots(16, 3) == [5, 5, 6] and synth.identity_slots(16, 4) == [5, 5, 2, 4]
+
+
+def test_clip_meta_oracle_known_answer():
+    """Hand-worked case of deepfakes_dataset.py:259-330: f=8, identity A owns 4 slots with 4 faces, identity B owns 4
+    slots with 2 faces (2 padded slots repeat B's last frame, get size 0 and mask 0)."""
+    from oracle.clip_meta_oracle import clip_meta
+    ids = [(4, [(3, 0), (5, 5), (9, 6), (12, 100)]), (4, [(5, 17), (9, 50)])]
+    se, mask, idm, pos = clip_meta(ids, 8, num_patches=2)
+    assert se.tolist() == [1, 1, 2, 20, 4, 10, 0, 0]
+    assert mask.tolist() == [True] * 6 + [False] * 2
+    assert idm[:4, :4].all() and idm[4:, 4:].all() and not idm[:4, 4:].any() and not idm[4:, :4].any()
+    # distinct frames sorted: 3, 5, 9, 12 -> ranks 1..4; slots: 3,5,9,12 | 5,9,9,9
+    ranks = [1, 2, 3, 4, 2, 3, 3, 3]
+    want = [0] + [t for r in ranks for t in ((r - 1) * 2 + 1, (r - 1) * 2 + 2)]
+    assert pos.tolist() == want
+    # identity attention off: every slot valid (deepfakes_dataset.py:285-286)
+    _, mask2, _, _ = clip_meta(ids, 8, num_patches=2, enable_identity_attention=False)
+    assert mask2.all()
+
+
+def test_clip_meta_oracle_agrees_with_synthetic_generator():
+    """synth.make_clip_meta (the bench / fixture input generator) and the line-by-line oracle describe the same
+    assembly: rebuild the generator's clips through the oracle."""
+    import numpy as np
+    from oracle.clip_meta_oracle import clip_meta
+    from mintime_b200 import synth
+    for n_id in (1, 2, 3, 4):
+        rng = np.random.default_rng(5 + n_id)
+        se, mask, idm, pos = synth.make_clip_meta(16, n_id, rng, pad_tail=True)
+        slots = synth.identity_slots(16, n_id)
+        ids, start = [], 0
+        ranks = ((pos[1::49] - 1) // 49 + 1).tolist()         # rank of each slot's frame
+        for ns in slots:
+            real = int(mask[start:start + ns].sum())
+            faces = [(ranks[start + i] * 10, int(se[start + i]) * 5) for i in range(real)]   # ratio 5*b -> bucket b
+            ids.append((ns, faces))
+            start += ns
+        se2, mask2, idm2, pos2 = clip_meta(ids, 16)
+        assert (se2 == se).all() and (mask2 == mask).all() and (idm2 == idm).all() and (pos2 == pos).all()
