@@ -158,22 +158,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int col = n0 + c + ob * 64;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              float u[8], gg[8];
+              float2 u2[4], g2[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { u[i] = __uint_as_float(ru[g * 8 + i]); gg[i] = __uint_as_float(rg[g * 8 + i]); }
+              for (int i = 0; i < 4; ++i) {
+                u2[i] = make_float2(__uint_as_float(ru[g * 8 + 2 * i]), __uint_as_float(ru[g * 8 + 2 * i + 1]));
+                g2[i] = make_float2(__uint_as_float(rg[g * 8 + 2 * i]), __uint_as_float(rg[g * 8 + 2 * i + 1]));
+              }
               if (e.bias) {
                 float b[8];
                 load8(e.bias + col + g * 8, b);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) u[i] += b[i];
+                for (int i = 0; i < 4; ++i) u2[i] = __fadd2_rn(u2[i], make_float2(b[2 * i], b[2 * i + 1]));
                 load8(e.bias + col + 32 + g * 8, b);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) gg[i] += b[i];
+                for (int i = 0; i < 4; ++i) g2[i] = __fadd2_rn(g2[i], make_float2(b[2 * i], b[2 * i + 1]));
               }
+              uint32_t o[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) u[i] *= fast_gelu(gg[i]);
-              *staging_piece(stg, trow, ob * 4 + g) =
-                  make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
+              for (int i = 0; i < 4; ++i) {
+                const float2 v = geglu2(u2[i], g2[i]);
+                o[i] = pack_bf16(v.x, v.y);
+              }
+              *staging_piece(stg, trow, ob * 4 + g) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         } else {
