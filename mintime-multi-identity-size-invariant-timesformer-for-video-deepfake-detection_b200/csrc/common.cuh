@@ -65,6 +65,15 @@ __device__ __forceinline__ float silu(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// bf16-path swish of (acc + shift) in the ONE form every epilogue of the library uses (scalar or packed FFMA2), so
+// that the kernel chosen for a shape (single-CTA / CTA-pair GEMM, fused or stand-alone depthwise) never changes a
+// bit of the result: h = fma(acc, 0.5, shift/2), h + h*tanh(h).
+__device__ __forceinline__ float swish_shift_fast(float acc, float shift) {
+  const float h = fmaf(acc, 0.5f, 0.5f * shift);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 template <bool kExact>
 __device__ __forceinline__ float sigmoidf_(float x) {
   if (kExact) return 1.0f / (1.0f + expf(-x));
@@ -133,16 +142,19 @@ struct GemmArgs {
 template <typename T, int KIND>
 __device__ __forceinline__ void epi_store8(const EpiParams& p, int row, int col, float (&v)[8]) {
   constexpr bool kExact = sizeof(T) == 4;
-  if (p.bias) {
-    float b[8];
-    load8(p.bias + col, b);
+  float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (p.bias) load8(p.bias + col, b);
+  if (KIND == EPI_STORE && p.act == 1 && !kExact) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = swish_shift_fast(v[i], b[i]);
+  } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += b[i];
   }
   if (KIND == EPI_STORE) {
-    if (p.act == 1) {
+    if (p.act == 1 && kExact) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = silu<kExact>(v[i]);
+      for (int i = 0; i < 8; ++i) v[i] = silu<true>(v[i]);
     }
     const size_t off = (size_t)row * p.ldo + col;
     if (p.resid) {

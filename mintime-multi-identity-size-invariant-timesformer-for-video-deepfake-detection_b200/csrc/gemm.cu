@@ -378,7 +378,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   for (int i = 0; i < 8; ++i) gg[i] += b[i];
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) u[i] *= fast_gelu(gg[i]);
+                for (int i = 0; i < 4; ++i) {       // same packed form as the CTA-pair kernel: identical bits
+                  const float2 r2 = geglu2(make_float2(u[2 * i], u[2 * i + 1]), make_float2(gg[2 * i], gg[2 * i + 1]));
+                  u[2 * i] = r2.x; u[2 * i + 1] = r2.y;
+                }
                 *staging_piece(stg, trow, ob * 4 + g) =
                     make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
               }
@@ -399,17 +402,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q][hh * 8 + i]);
-                if (e.bias && col < p.N) {
-                  float b[8];
-                  load8(e.bias + col, b);
+                float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (e.bias && col < p.N) load8(e.bias + col, b);
+                if (KIND == EPI_STORE && e.act == 1) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = swish_shift_fast(v[i], b[i]);
+                } else {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] += b[i];
                 }
                 if (KIND == EPI_STORE) {
-                  if (e.act == 1) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = silu<false>(v[i]);
-                  }
                   *staging_piece(stg, trow, q * 2 + hh) =
                       make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 } else {                            // EPI_RESID_F32: 8 fp32 = two 16-byte pieces

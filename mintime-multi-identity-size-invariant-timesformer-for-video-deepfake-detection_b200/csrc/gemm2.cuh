@@ -196,17 +196,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q][hh * 8 + i]);
-              if (e.bias) {
-                float b[8];
-                load8(e.bias + col, b);
+              float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (e.bias) load8(e.bias + col, b);
+              if (KIND == EPI_STORE && e.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = swish_shift_fast(v[i], b[i]);
+              } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] += b[i];
               }
               if (KIND == EPI_STORE) {
-                if (e.act == 1) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = silu<false>(v[i]);
-                }
                 *staging_piece(stg, trow, q * 2 + hh) =
                     make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
               } else {

@@ -544,3 +544,32 @@ def test_cuda_graph_capture_replays_bit_exact():
         logits_e, (sa_e, ta_e) = fwd()
         torch.cuda.synchronize()
     assert torch.equal(got[0], logits_e) and torch.equal(got[1], sa_e) and torch.equal(got[2], ta_e)
+
+
+@pytest.mark.gpu
+def test_logits_do_not_depend_on_the_batch_a_clip_is_in():
+    """A clip alone (B=1: single-CTA GEMM kernels, 785 token rows) and the same clip inside a batch of 9 (CTA-pair
+    GEMM kernels above 4096 rows, other tile <-> block assignments everywhere) must give the same logits and
+    attention maps BIT FOR BIT: every epilogue uses one arithmetic form and every reduction a fixed order."""
+    f = 16
+    cfg = spec.default_tsf_config(num_frames=f)
+    ext = EfficientNet.from_name("efficientnet-b0", precision="bf16")
+    ext.load_state_dict(synth.make_effnet_state_dict(1234)); ext = ext.to(DEV).eval()
+    model = SizeInvariantTimeSformer(config=cfg, require_attention=True, precision="bf16")
+    model.load_state_dict(synth.make_tsf_state_dict(cfg, 4321)); model = model.to(DEV).eval()
+    meta = synth.make_batch_meta(9, f, [1, 2, 3, 4], seed=7)
+    frames = synth.make_frames(9, f, seed=7, mask=meta["mask"], dtype=torch.uint8).to(DEV)
+
+    def run(idx):
+        m = {k: v[idx].to(DEV) for k, v in meta.items()}
+        x = frames[idx].reshape(-1, 224, 224, 3).permute(0, 3, 1, 2)
+        with torch.no_grad():
+            return model(ext(x).reshape(len(idx), f, 1280, 7, 7), mask=m["mask"], size_embedding=m["size_embedding"],
+                         identities_mask=m["identities_mask"], positions=m["positions"])
+
+    logits, (sa, ta) = run(list(range(9)))
+    for i in (0, 5, 8):
+        l1, (s1, t1) = run([i])
+        torch.cuda.synchronize()
+        assert torch.equal(l1[0], logits[i]), (i, l1[0].item(), logits[i].item())
+        assert torch.equal(s1, sa[i * 8:(i + 1) * 8]) and torch.equal(t1, ta[i * 8:(i + 1) * 8])
