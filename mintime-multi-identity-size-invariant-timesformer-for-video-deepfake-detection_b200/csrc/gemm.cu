@@ -480,37 +480,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m0 + r;
       const int img = (row < p.M ? row : p.M - 1) / p.rows_per_gate;
       const float* grow = p.gate + (size_t)img * p.K;   // global row (fallback when the gates are not staged)
-      const float* gsm = nullptr;
+      const bf16* gsm = nullptr;
       if (p.gate_imgs > 0) {
+        // staged gates are held as bf16 so that the scaling is one packed HMUL2 per channel pair (the fp32 form
+        // costs 5x the instructions and made the gate warps the bottleneck of the long-K project convs:
+        // 49.6 vs 26.7 us ungated at K = 1152, N = 192)
         const int img0 = m0 / p.rows_per_gate;
         const int img1 = min(m0 + kBlockM - 1, p.M - 1) / p.rows_per_gate;
         asm volatile("bar.sync 2, 128;" ::: "memory");   // everyone is done with the previous tile's gates
         const float4* src = reinterpret_cast<const float4*>(p.gate + (size_t)img0 * p.K);
         const int n4 = (img1 - img0 + 1) * (p.K >> 2);
-        for (int i = r; i < n4; i += 128) reinterpret_cast<float4*>(gate_s)[i] = src[i];
+        bf16* gs = reinterpret_cast<bf16*>(gate_s);
+        for (int i = r; i < n4; i += 128) {
+          const float4 g4 = src[i];
+          *reinterpret_cast<uint2*>(gs + 4 * i) = make_uint2(pack_bf16(g4.x, g4.y), pack_bf16(g4.z, g4.w));
+        }
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        gsm = gate_s + (size_t)(img - img0) * p.K;
+        gsm = gs + (size_t)(img - img0) * p.K;
       }
       for (int kb = 0; kb < num_kb; ++kb) {
-        const float* gk = (gsm ? gsm : grow) + kb * kBlockK;
+        if (gsm) {
+          ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
+          uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
+          const bf16* gk = gsm + kb * kBlockK;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (kb * kBlockK + c * 8 < p.K) {
+              const uint4 gq = *reinterpret_cast<const uint4*>(gk + c * 8);
+              uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
+              uint4 u = *ptr;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h[i] = __hmul2(h[i], gh[i]);
+              *ptr = u;
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&gated_bar[ps.stage]);
+          ps.advance(p.stages);
+          continue;
+        }
+        const float* gk = grow + kb * kBlockK;
         // gates not staged (single k-block shapes): fetch the first half of the row's gates BEFORE waiting for the
         // TMA so that their L2 latency overlaps the load
         float4 pre[8];
-        if (!gsm) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (kb * kBlockK + c * 8 < p.K) {
-              pre[2 * c] = *reinterpret_cast<const float4*>(gk + c * 8);
-              pre[2 * c + 1] = *reinterpret_cast<const float4*>(gk + c * 8 + 4);
-            }
-        }
+        for (int c = 0; c < 4; ++c)
+          if (kb * kBlockK + c * 8 < p.K) {
+            pre[2 * c] = *reinterpret_cast<const float4*>(gk + c * 8);
+            pre[2 * c + 1] = *reinterpret_cast<const float4*>(gk + c * 8 + 4);
+          }
         ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
         uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int k = kb * kBlockK + c * 8;
           if (k < p.K) {
-            const bool use_pre = !gsm && c < 4;
+            const bool use_pre = c < 4;
             const float4 g0 = use_pre ? pre[2 * (c & 3)] : *reinterpret_cast<const float4*>(gk + c * 8);
             const float4 g1 = use_pre ? pre[2 * (c & 3) + 1] : *reinterpret_cast<const float4*>(gk + c * 8 + 4);
             uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
@@ -712,9 +739,9 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   // SE gates staged per tile: a 128-row tile touches at most (127 / rows_per_gate) + 2 images
   p.gate_imgs = 0;
   int gate_bytes = 0;
-  if (GATED && kEW == 8 && g.K % 4 == 0 && num_kb >= 2) {
+  if (GATED && kEW == 8 && g.K % 8 == 0 && num_kb >= 2) {
     const int imgs = (kBlockM - 1) / g.rows_per_gate + 2;
-    if (imgs * g.K * 4 <= 20 * 1024) { p.gate_imgs = imgs; gate_bytes = imgs * g.K * 4; }
+    if (imgs * g.K * 2 <= 20 * 1024) { p.gate_imgs = imgs; gate_bytes = (imgs * g.K * 2 + 15) & ~15; }
   }
   const int fixed = (TMA_OUT ? 2 * kStagingBytes : 0) + 1024 /*align slack*/ + (3 * kMaxStages + 5) * 8 + 16 + bias_bytes +
                     gate_bytes + (p.b_resident ? num_kb * b_block : 0);
