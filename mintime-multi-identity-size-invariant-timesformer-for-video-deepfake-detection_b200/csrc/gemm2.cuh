@@ -297,7 +297,9 @@ int launch_tc2(const GemmArgs& g, cudaStream_t stream) {
 inline bool tc2_eligible(const GemmArgs& g) {
   if (g.gate || g.epi.resid) return false;
   if (g.epi.kind != EPI_STORE && g.epi.kind != EPI_GEGLU && g.epi.kind != EPI_RESID_F32) return false;
-  if (g.N % 256 != 0 || g.M < 4096 || g.K < 64) return false;
+  // (K < 384: the pair kernel's longer prologue / epilogue per tile does not pay: the 320 -> 1280 head conv runs
+  // 43 us on the single-CTA kernel against 70 us here)
+  if (g.N % 256 != 0 || g.M < 4096 || g.K < 384) return false;
   if ((g.epi.ldo * (g.epi.kind == EPI_RESID_F32 ? 4 : 2)) % 16 != 0 || (reinterpret_cast<uintptr_t>(g.epi.out) & 15)) return false;
   return true;
 }
