@@ -1,0 +1,76 @@
+"""CUDA-graph replay of the hot path for a fixed batch shape.
+
+The reference serves one video at a time (predict.py:394-417: b = 1, 8..32 faces).  At that size the ~185 kernel
+launches of EfficientNet-B0 -> SizeInvariantTimeSformer cost more host time (launch + TMA descriptor encoding) than
+GPU time, so the latency-critical entry point captures them ONCE into a CUDA graph -- possible because nothing behind
+the C ABI allocates or synchronises -- and replays the graph per clip.  Results are bit-identical to the eager
+modules (tests/test_gpu_parity.py::test_graphed_hot_path).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+class GraphedHotPath:
+    """extractor + model captured for (batch, num_frames) clips of 224x224 faces.
+
+    ``__call__(videos, mask, identities_mask, size_embedding, positions)`` takes the tensors of the reference loop
+    (videos (b,f,224,224,3) raw 0..255, uint8 or float32, host or device) and returns ``logits`` or
+    ``(logits, [space_attn, time_attn])`` like ``SizeInvariantTimeSformer.forward``; the returned tensors are the
+    graph's static outputs and are overwritten by the next call.
+    """
+
+    def __init__(self, extractor, model, batch: int, num_frames: int, frame_dtype=torch.uint8, device="cuda:0",
+                 num_patches: int = 49):
+        self.device = torch.device(device)
+        _lib.require_device(self.device)
+        self.ext, self.model = extractor, model
+        self.b, self.f = batch, num_frames
+        d = self.device
+        self.static: Dict[str, torch.Tensor] = {
+            "videos": torch.zeros((batch, num_frames, 224, 224, 3), dtype=frame_dtype, device=d),
+            "mask": torch.ones((batch, num_frames), dtype=torch.bool, device=d),
+            "identities_mask": torch.ones((batch, num_frames, num_frames), dtype=torch.bool, device=d),
+            "size_embedding": torch.ones((batch, num_frames), dtype=torch.int32, device=d),
+            "positions": torch.arange(1 + num_frames * num_patches, dtype=torch.int64, device=d).repeat(batch, 1),
+        }
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.out = None
+        self._capture()
+
+    def _forward(self):
+        s = self.static
+        x = s["videos"].view(self.b * self.f, 224, 224, 3).permute(0, 3, 1, 2)          # train.py:341
+        feats = self.ext(x)
+        feats = feats.reshape(self.b, self.f, *feats.shape[1:])                           # train.py:354
+        return self.model(feats, mask=s["mask"], size_embedding=s["size_embedding"],
+                          identities_mask=s["identities_mask"], positions=s["positions"])
+
+    def _capture(self):
+        with torch.no_grad(), torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                  # warm-up: weight packing, one-time function attributes
+                    self._forward()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._forward()
+
+    def __call__(self, videos: torch.Tensor, mask: torch.Tensor, identities_mask: torch.Tensor,
+                 size_embedding: torch.Tensor, positions: torch.Tensor):
+        s = self.static
+        if tuple(videos.shape) != tuple(s["videos"].shape):
+            raise ValueError(f"graph captured for {tuple(s['videos'].shape)}, got {tuple(videos.shape)}")
+        s["videos"].copy_(videos, non_blocking=True)
+        s["mask"].copy_(mask, non_blocking=True)
+        s["identities_mask"].copy_(identities_mask, non_blocking=True)
+        s["size_embedding"].copy_(size_embedding, non_blocking=True)
+        s["positions"].copy_(positions, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -573,3 +573,28 @@ def test_logits_do_not_depend_on_the_batch_a_clip_is_in():
         torch.cuda.synchronize()
         assert torch.equal(l1[0], logits[i]), (i, l1[0].item(), logits[i].item())
         assert torch.equal(s1, sa[i * 8:(i + 1) * 8]) and torch.equal(t1, ta[i * 8:(i + 1) * 8])
+
+
+@pytest.mark.gpu
+def test_graphed_hot_path():
+    """mintime_b200.graphed.GraphedHotPath (the single-video serving entry point: one CUDA graph replay per clip)
+    returns exactly what the eager modules return, for successive clips through the same graph."""
+    from mintime_b200.graphed import GraphedHotPath
+    cfg, esd, tsd, meta, frames = case_inputs("cfg1_b1_f8_id1")
+    B, f = frames.shape[:2]
+    ext = EfficientNet.from_name("efficientnet-b0", precision="bf16"); ext.load_state_dict(esd); ext = ext.to(DEV).eval()
+    model = SizeInvariantTimeSformer(config=cfg, require_attention=True, precision="bf16")
+    model.load_state_dict(tsd); model = model.to(DEV).eval()
+    hot = GraphedHotPath(ext, model, B, f, frame_dtype=torch.float32, device=DEV)
+    for trial in range(2):
+        vid = frames if trial == 0 else torch.flip(frames, dims=[1])
+        logits_g, (sa_g, ta_g) = hot(vid, meta["mask"], meta["identities_mask"], meta["size_embedding"], meta["positions"])
+        torch.cuda.synchronize()
+        got = (logits_g.clone(), sa_g.clone(), ta_g.clone())
+        with torch.no_grad():
+            x = vid.to(DEV).view(B * f, 224, 224, 3).permute(0, 3, 1, 2)
+            le, (se_, te) = model(ext(x).reshape(B, f, 1280, 7, 7), mask=meta["mask"].to(DEV),
+                                  size_embedding=meta["size_embedding"], identities_mask=meta["identities_mask"].to(DEV),
+                                  positions=meta["positions"].to(DEV))
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], le) and torch.equal(got[1], se_) and torch.equal(got[2], te)
