@@ -127,7 +127,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         if name.endswith("_fwd"):
             fn.restype = i32
-    if lib.mt_abi_version() != 1:
+    if lib.mt_abi_version() != 2:
         raise RuntimeError("mintime_b200: ABI version mismatch between _lib.py and libmintime_b200.so")
     _lib = lib
     return lib
