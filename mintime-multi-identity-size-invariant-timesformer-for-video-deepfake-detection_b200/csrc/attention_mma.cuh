@@ -126,6 +126,97 @@ __device__ __forceinline__ void attend_mtile(uint8_t* qs, uint8_t* ks, uint8_t* 
   __syncwarp();
 }
 
+// One 16-query m-tile against KT*16 patch keys (tile rows 1 .. KT*16) PLUS the CLS key (tile row 0) handled apart:
+// with f = 16 frames the 17 keys of a time group would otherwise pad to two 16-key tiles (32 mma per group); here
+// the frame keys are exactly KT tiles (QK^T and PV on mma.sync), the CLS key's score comes from KT-independent 4 mma
+// with k_cls broadcast over the B columns, and its value row is added as a rank-1 update in registers (20 mma).
+//   allow(q_local, key) as in attend_mtile: key 0 = CLS (always allowed by the callers), key k+1 = frame k.
+template <int KT, typename Allow>
+__device__ __forceinline__ void attend_mtile_cls_apart(uint8_t* qs, uint8_t* ks, uint8_t* vs, int q_row0, int lane, Allow allow) {
+  constexpr int NT = KT * 2;
+  const int g = lane >> 2, t = lane & 3;
+  float s[NT][4], sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {              // 16 head dims per step
+    uint32_t a[4];
+    ldmatrix_x4(a, smem_u32(tile_ptr(qs, q_row0 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4))));
+#pragma unroll
+    for (int jp = 0; jp < KT; ++jp) {
+      uint32_t b[4];
+      ldmatrix_x4(b, smem_u32(tile_ptr(ks, 1 + jp * 16 + (lane & 7) + (lane >> 4) * 8, kk * 2 + ((lane >> 3) & 1))));
+      mma_bf16(s[jp * 2], a, b[0], b[1]);
+      mma_bf16(s[jp * 2 + 1], a, b[2], b[3]);
+    }
+    // CLS key: every B column = k_cls, so c0 / c2 of every lane = q_row . k_cls for rows g / g + 8
+    const uint32_t kb0 = *reinterpret_cast<const uint32_t*>(tile_ptr(ks, 0, kk * 2) + t * 4);
+    const uint32_t kb1 = *reinterpret_cast<const uint32_t*>(tile_ptr(ks, 0, kk * 2 + 1) + t * 4);
+    mma_bf16(sc, a, kb0, kb1);
+  }
+  float mx0 = sc[0], mx1 = sc[2];               // the CLS key is always allowed: it keeps every row's max finite
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = 1 + j * 8 + t * 2 + e;
+      if (!allow(g, key)) s[j][e] = -FLT_MAX;
+      if (!allow(g + 8, key)) s[j][2 + e] = -FLT_MAX;
+      mx0 = fmaxf(mx0, s[j][e]);
+      mx1 = fmaxf(mx1, s[j][2 + e]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      s[j][e] = __expf(s[j][e] - mx0);           // masked entries (-FLT_MAX) underflow to exactly 0
+      s[j][2 + e] = __expf(s[j][2 + e] - mx1);
+      sum0 += s[j][e];
+      sum1 += s[j][2 + e];
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float ec0 = __expf(sc[0] - mx0), ec1 = __expf(sc[2] - mx1);   // CLS key, counted once per row
+  const float inv0 = 1.0f / (sum0 + ec0), inv1 = 1.0f / (sum1 + ec1);
+  // P in bf16 for the tensor-core product; the CLS probability goes through bf16 as well so that every key is
+  // weighted at the same precision
+  const float pc0 = __bfloat162float(__float2bfloat16_rn(ec0 * inv0)), pc1 = __bfloat162float(__float2bfloat16_rn(ec1 * inv1));
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {                 // rank-1 start: o = p_cls * v_cls
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(tile_ptr(vs, 0, j) + t * 4);
+    const float v0 = __uint_as_float(v << 16), v1 = __uint_as_float(v & 0xffff0000u);
+    o[j][0] = pc0 * v0; o[j][1] = pc0 * v1; o[j][2] = pc1 * v0; o[j][3] = pc1 * v1;
+  }
+#pragma unroll
+  for (int kk = 0; kk < KT; ++kk) {             // 16 frame keys per step
+    uint32_t a[4];
+    a[0] = pack2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+    a[1] = pack2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+    a[2] = pack2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+    a[3] = pack2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, smem_u32(tile_ptr(vs, 1 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4))));
+      mma_bf16(o[dp * 2], a, b[0], b[1]);
+      mma_bf16(o[dp * 2 + 1], a, b[2], b[3]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(tile_ptr(qs, q_row0 + g, j) + t * 4) = pack2(o[j][0], o[j][1]);
+    *reinterpret_cast<uint32_t*>(tile_ptr(qs, q_row0 + g + 8, j) + t * 4) = pack2(o[j][2], o[j][3]);
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // CLS row of Attention.forward (:117-120): query 0 of each (b, h) attends ALL N keys with the padded-frame
 // mask (cls_attn_mask :258-260).  The grouped kernels already hold every patch key/value of their group in
@@ -383,12 +474,17 @@ __global__ void __launch_bounds__(256) attn_time_mma_kernel(const bf16* __restri
                           cls_scores ? cls_scores + (size_t)bh * N : nullptr);
     return;
   }
+  auto allow = [&](int mt, int ql, int key) {
+    const int q = mt * 16 + ql;
+    return q < f ? ((allow_bits[q] >> key) & 1ull) != 0 : key == 0;
+  };
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    attend_mtile<NKT>(qs, ks, vs, mt * 16, lane, [&](int ql, int key) {
-      const int q = mt * 16 + ql;
-      return q < f ? ((allow_bits[q] >> key) & 1ull) != 0 : key == 0;
-    });
+    // f a multiple of 16: the frame keys fill (NKT - 1) whole tiles and the CLS key is handled apart
+    if (f == (NKT - 1) * 16 && NKT >= 2)
+      attend_mtile_cls_apart<(NKT >= 2 ? NKT - 1 : 1)>(qs, ks, vs, mt * 16, lane, [&](int ql, int key) { return allow(mt, ql, key); });
+    else
+      attend_mtile<NKT>(qs, ks, vs, mt * 16, lane, [&](int ql, int key) { return allow(mt, ql, key); });
   }
   for (int e = lane; e < MT * 16 * 8; e += 32) {
     const int r = e >> 3, c = e & 7;
