@@ -40,6 +40,7 @@ class GraphedHotPath:
         }
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.out = None
+        self.kernels_per_replay = 0      # kernels of this library inside the graph
         self._capture()
 
     def _forward(self):
@@ -59,8 +60,16 @@ class GraphedHotPath:
                     self._forward()
             torch.cuda.current_stream().wait_stream(side)
             self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.load().mt_prof_launch_count()
             with torch.cuda.graph(self.graph):
                 self.out = self._forward()
+            self.kernels_per_replay = int(_lib.load().mt_prof_launch_count() - n0)
+
+    def replay(self):
+        """Replay the captured graph on whatever ``self.static`` holds (pipelined feeding: fill ``static`` from a
+        copy stream, make the current stream wait for it, then call this); returns the static outputs."""
+        self.graph.replay()
+        return self.out
 
     def __call__(self, videos: torch.Tensor, mask: torch.Tensor, identities_mask: torch.Tensor,
                  size_embedding: torch.Tensor, positions: torch.Tensor):
