@@ -331,7 +331,7 @@ int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, i
     const int grid = B * heads * ((n + 3) / 4);
     auto launch_time = [&](auto kern, int nkt, int mt_) -> int {
       const size_t dyn = 4 * (size_t)(mt_ * 16 * 128 + 2 * nkt * 16 * 128);
-      if (dyn > 48 * 1024) {
+      if (dyn > 40 * 1024) {                     // (the kernel also has ~3 KiB of static shared memory)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(attn_time)");
       }

@@ -122,7 +122,7 @@ def test_layernorm(prec):
 
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("mode", ["time", "space"])
-@pytest.mark.parametrize("B,f", [(3, 16), (2, 8)])
+@pytest.mark.parametrize("B,f", [(3, 16), (2, 8), (2, 32), (1, 12), (2, 20)])
 def test_divided_attention_core(prec, mode, B, f):
     n, heads, dh = 49, 8, 64
     N = 1 + f * n
