@@ -169,8 +169,12 @@ class SizeInvariantTimeSformer(nn.Module):
         # token layout 'b (f h w) c' (:227).  The extractor shim already produces this memory order, so
         # this is a view; a true (b,f,c,h,w)-contiguous input costs one transposing copy (plumbing).
         tok = x.permute(0, 1, 3, 4, 2)
-        if tok.dtype != T or not tok.is_contiguous():
-            tok = tok.to(dtype=T, memory_format=torch.contiguous_format)
+        if tok.dtype != T:
+            tok = tok.to(dtype=T)
+        if not tok.is_contiguous():
+            # (Tensor.to(dtype, memory_format=contiguous_format) returns the SAME strided tensor when the dtype
+            # already matches, so the copy has to be explicit)
+            tok = tok.contiguous()
         mask_u8 = mask.to(device=dev, dtype=torch.uint8).contiguous()
         idm_u8 = identities_mask.to(device=dev, dtype=torch.uint8).contiguous()
         if mask_u8.shape != (b, f) or idm_u8.shape != (b, f, f):

@@ -421,6 +421,38 @@ def test_transformer_matches_oracle_on_same_features(prec, oracle_features):
         assert rel_err(sa.cpu(), ref_sa) <= 5e-3 and rel_err(ta.cpu(), ref_ta) <= 5e-3
 
 
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("f,ids", [(32, [3, 1]), (16, [4, 2, 1]), (8, [2])])
+def test_transformer_other_frame_counts(prec, f, ids):
+    """num-frames 8 / 16 / 32 are the values train.py:101 accepts: the transformer on seeded features with
+    multi-identity masks and padded slots, against the oracle (f = 32 exercises the 2-tile time-attention path and
+    the 1569-token CLS row)."""
+    B = len(ids)
+    cfg = spec.default_tsf_config(num_frames=f)
+    tsd = synth.make_tsf_state_dict(cfg, 99)
+    meta = synth.make_batch_meta(B, f, ids, seed=f)
+    g = torch.Generator().manual_seed(f)
+    feats = torch.nn.functional.silu(torch.randn((B, f, 1280, 7, 7), generator=g)) * 20.0
+    feats = feats.bfloat16().float()                      # identical inputs for both precisions
+    with torch.no_grad():
+        ref_logits, (ref_sa, ref_ta) = orc.tsf_forward(tsd, cfg, feats, meta["mask"], meta["identities_mask"],
+                                                       meta["size_embedding"], meta["positions"])
+    model = SizeInvariantTimeSformer(config=cfg, require_attention=True, precision=prec)
+    model.load_state_dict(tsd)
+    model = model.to(DEV).eval()
+    x = feats.to(DEV) if prec == "fp32" else feats.to(DEV).bfloat16()
+    with torch.no_grad():
+        logits, (sa, ta) = model(x, mask=meta["mask"].to(DEV), size_embedding=meta["size_embedding"],
+                                 identities_mask=meta["identities_mask"].to(DEV), positions=meta["positions"].to(DEV))
+    torch.cuda.synchronize()
+    if prec == "fp32":
+        assert torch.allclose(logits.cpu(), ref_logits, rtol=1e-3, atol=1e-4)
+        assert rel_err(sa.cpu(), ref_sa) <= 1e-3 and rel_err(ta.cpu(), ref_ta) <= 1e-3
+    else:
+        assert (logits.cpu() - ref_logits).abs().max() <= 1e-2
+        assert rel_err(sa.cpu(), ref_sa) <= 5e-3 and rel_err(ta.cpu(), ref_ta) <= 5e-3
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def _models(prec, f=16):
     cfg = spec.default_tsf_config(num_frames=f)
