@@ -453,6 +453,58 @@ def test_transformer_other_frame_counts(prec, f, ids):
         assert rel_err(sa.cpu(), ref_sa) <= 5e-3 and rel_err(ta.cpu(), ref_ta) <= 5e-3
 
 
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("pos_on,size_on", [(False, True), (True, False), (False, False)])
+def test_transformer_embedding_switches(prec, pos_on, size_on):
+    """enable-pos-emb off -> arange positions (size_invariant_timesformer.py:237-238); enable-size-emb off -> no size
+    table at all (:241): both switches of config/size_invariant_timesformer.yaml against the oracle."""
+    f, B = 8, 2
+    cfg = spec.default_tsf_config(num_frames=f)
+    cfg["model"]["enable-pos-emb"] = pos_on
+    cfg["model"]["enable-size-emb"] = size_on
+    tsd = synth.make_tsf_state_dict(cfg, 5)
+    meta = synth.make_batch_meta(B, f, [2, 1], seed=21)
+    g = torch.Generator().manual_seed(3)
+    feats = (torch.nn.functional.silu(torch.randn((B, f, 1280, 7, 7), generator=g)) * 20.0).bfloat16().float()
+    with torch.no_grad():
+        ref_logits, (ref_sa, ref_ta) = orc.tsf_forward(tsd, cfg, feats, meta["mask"], meta["identities_mask"],
+                                                       meta["size_embedding"], meta["positions"])
+    model = SizeInvariantTimeSformer(config=cfg, require_attention=True, precision=prec)
+    model.load_state_dict(tsd)
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        logits, (sa, ta) = model(feats.to(DEV), mask=meta["mask"].to(DEV),
+                                 size_embedding=meta["size_embedding"] if size_on else None,
+                                 identities_mask=meta["identities_mask"].to(DEV),
+                                 positions=meta["positions"].to(DEV) if pos_on else None)
+    torch.cuda.synchronize()
+    if prec == "fp32":
+        assert torch.allclose(logits.cpu(), ref_logits, rtol=1e-3, atol=1e-4)
+        assert rel_err(sa.cpu(), ref_sa) <= 1e-3 and rel_err(ta.cpu(), ref_ta) <= 1e-3
+    else:
+        assert (logits.cpu() - ref_logits).abs().max() <= 1e-2
+        assert rel_err(sa.cpu(), ref_sa) <= 5e-3 and rel_err(ta.cpu(), ref_ta) <= 5e-3
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_extractor_input_layouts_and_batch_independence(u8):
+    """The extractor takes the permuted NHWC view the reference loop builds (train.py:341) as well as true NCHW
+    memory, float32 or uint8, and an image's features do not depend on the images it is batched with (bit exact)."""
+    esd = synth.make_effnet_state_dict(1234)
+    ext = EfficientNet.from_name("efficientnet-b0", precision="bf16")
+    ext.load_state_dict(esd); ext = ext.to(DEV).eval()
+    frames = synth.make_frames(1, 5, seed=4, dtype=torch.uint8)[0]            # (5,224,224,3) uint8 NHWC
+    x_nhwc = frames.to(DEV) if u8 else frames.to(DEV).float()
+    with torch.no_grad():
+        a = ext(x_nhwc.permute(0, 3, 1, 2))                                    # view of NHWC memory
+        b = ext(x_nhwc.permute(0, 3, 1, 2).contiguous())                       # true NCHW memory
+        one = ext(x_nhwc[3:4].permute(0, 3, 1, 2))                             # image 3 alone
+    torch.cuda.synchronize()
+    assert a.shape == (5, 1280, 7, 7)
+    assert torch.equal(a, b)
+    assert torch.equal(a[3:4], one)
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def _models(prec, f=16):
     cfg = spec.default_tsf_config(num_frames=f)
