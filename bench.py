@@ -48,7 +48,7 @@ class ClockSampler:
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.index = index
-        self.window = "timed region"
+        self.window = "warm-up + timed region"
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -56,7 +56,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "20"],
+                                          "-i", str(self.index), "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -312,11 +312,11 @@ def main():
 
     lib = _lib.load()
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # before the warm-up: nvidia-smi's own start-up (NVML init) stays out of the timed region
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
     launches0 = lib.mt_prof_launch_count()
     t_wall = time.perf_counter()
     ms = timed(step_resident, args.steps, 0)
@@ -326,7 +326,7 @@ def main():
     if rank == 0 and time.perf_counter() - t_wall < 0.4:
         # nvidia-smi cannot sample faster than ~20 ms: keep the SAME step running (untimed) until the poller has
         # seen at least ~0.4 s of load, so the clocks / throttle reasons describe this workload
-        sampler.window = "timed region + untimed continuation of the same step (region shorter than the poller needs)"
+        sampler.window = "warm-up + timed region + untimed continuation of the same step (region shorter than the poller needs)"
         while time.perf_counter() - t_wall < 0.4:
             step_resident()
             torch.cuda.synchronize()
