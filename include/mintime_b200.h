@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-#define MT_ABI_VERSION 2   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd */
+#define MT_ABI_VERSION 3   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
+                            * 3: + the backward entry points of the transformer (mt_*_bwd, mt_grad_prep, mt_geglu_*) */
 
 enum { MT_PREC_FP32 = 0, MT_PREC_BF16 = 1 };
 enum { MT_OK = 0, MT_ERR_ARG = -1, MT_ERR_WORKSPACE = -2, MT_ERR_UNSUPPORTED = -3, MT_ERR_DRIVER = -4 };
@@ -234,6 +235,56 @@ int mt_head_fwd(const float* x, const float* ln_g, const float* ln_b, const floa
  * the time map and their sum.  space_attn/time_attn f32 [batch*heads][tokens] -> out f32 [batch][3][num_frames]. */
 int mt_aggregate_attn_fwd(const float* space_attn, const float* time_attn, float* out, int batch, int heads,
                           int num_frames, int tokens, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward pass of the transformer: `loss.backward()` of train.py:376-378 for SizeInvariantTimeSformer with a frozen
+ * extractor (train.py:344-346).  The two contractions of every Linear reuse the forward GEMMs:
+ *   dgrad  dX[m][k]  = dY[m][n] * W[n][k]      -> mt_pointwise_fwd(a = dY, w = W^T stored [k][n])
+ *   wgrad  dW[n][k] += dY^T * X                -> mt_linear_residual_fwd(a = dY^T [n][mp], w = X^T [k][mp], x = dW f32)
+ * with the transposed operands produced by mt_grad_prep.  mintime_b200/training.py holds the schedule.
+ * ------------------------------------------------------------------------------------------- */
+
+/* One pass over src [m][c] (f32 when src_is_f32, else T) producing any of: out_rm T [m][c] (cast), out_t T [c][mp]
+ * (transpose; columns m..mp-1 zero; mp a multiple of 64), colsum f32 [c] (column sums = the bias gradient when src is
+ * dY).  rows_per_batch > 0 skips the CLS row of every video: source row = i + i / rows_per_batch + 1.
+ * workspace: mt_grad_prep_workspace_bytes(mp, c) bytes when colsum is requested. */
+size_t mt_grad_prep_workspace_bytes(int m, int c);
+int mt_grad_prep(int precision, const void* src, int src_is_f32, void* out_rm, void* out_t, float* colsum, int m, int c,
+                 int mp, int rows_per_batch, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[c] (+)= sum_r in[r][c], fixed summation order. */
+int mt_colsum_f32(const float* in, float* out, int rows, int cols, int accumulate, void* stream);
+
+/* nn.LayerNorm backward of a PreNorm sub-block (size_invariant_timesformer.py:18-26): gx[rows][dim] (f32 gradient of the
+ * residual stream) += dLN(dy);  dgamma_dbeta f32 [2*dim] = (dgamma | dbeta) (assigned). */
+size_t mt_layernorm_bwd_workspace_bytes(int rows, int dim);
+int mt_layernorm_bwd(int precision, const float* x, const float* gamma, const void* dy, float* gx, float* dgamma_dbeta,
+                     int rows, int dim, void* workspace, size_t workspace_bytes, void* stream);
+
+/* GEGLU on a stored pre-activation h T [m][2*n_out] in the interleaved column order of mt_ff_weights_t.w1
+ * (size_invariant_timesformer.py:60-63): out T [m][n_out] = u * gelu_erf(g); backward: dh T [m][2*n_out] same order.
+ * (The training forward keeps h; inference uses the fused mt_linear_geglu_fwd.) */
+int mt_geglu_fwd(int precision, const void* h, void* out, int m, int n_out, void* stream);
+int mt_geglu_bwd(int precision, const void* h, const void* dout, void* dh, int m, int n_out, void* stream);
+
+/* Backward of mt_divided_attn_fwd: qkv, mask, identities_mask as in the forward (probabilities are recomputed),
+ * dout T [B][1+f*n][heads*dim_head] -> dqkv T [B][1+f*n][3*heads*dim_head] (every element written). */
+size_t mt_divided_attn_bwd_workspace_bytes(int batch, int f, int n, int heads);
+int mt_divided_attn_bwd(int precision, const void* qkv, const void* dout, const uint8_t* mask,
+                        const uint8_t* identities_mask, int mode, void* dqkv, int batch, int f, int n, int heads,
+                        int dim_head, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the token build (:225-248) w.r.t. the embedding tables and the CLS token: g0 f32 [B][1+f*n][dim] is
+ * scattered (+=, fp32 atomics) into dpos / dsize (table-shaped, may be NULL) and dcls [dim]; the caller zeroes them. */
+int mt_embed_bwd(const float* g0, const int64_t* positions, const int32_t* size_embedding, float* dpos, float* dsize,
+                 float* dcls, int batch, int f, int n, int dim, void* stream);
+
+/* Backward of mt_head_fwd: gx[b][0][:] = dL/dx[b][0] (assigned; the other rows of gx are the caller's to zero);
+ * grads f32 [classes*dim + classes + 2*dim] = (dW | dbias | dgamma | dbeta). */
+size_t mt_head_bwd_workspace_bytes(int batch, int dim, int num_classes);
+int mt_head_bwd(const float* x, const float* ln_g, const float* ln_b, const float* w, const float* dlogits, float* gx,
+                float* grads, int batch, int tokens, int dim, int num_classes, void* workspace, size_t workspace_bytes,
+                void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Diagnostics (used by bench.py; off by default, no effect on results)

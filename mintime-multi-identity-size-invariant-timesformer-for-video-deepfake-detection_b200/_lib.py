@@ -22,7 +22,10 @@ EXPORTS = [
     "mt_pointwise_fwd", "mt_linear_residual_fwd", "mt_linear_geglu_fwd", "mt_patch_embed_fwd",
     "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
     "mt_dwconv_chunks", "mt_dwconv_se_fwd", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
-    "mt_aggregate_attn_fwd", "mt_clip_meta_fwd", "mt_prof_enable", "mt_prof_reset", "mt_prof_collect", "mt_prof_launch_count",
+    "mt_aggregate_attn_fwd", "mt_clip_meta_fwd",
+    "mt_grad_prep_workspace_bytes", "mt_grad_prep", "mt_colsum_f32", "mt_layernorm_bwd_workspace_bytes", "mt_layernorm_bwd",
+    "mt_geglu_fwd", "mt_geglu_bwd", "mt_divided_attn_bwd_workspace_bytes", "mt_divided_attn_bwd", "mt_embed_bwd",
+    "mt_head_bwd_workspace_bytes", "mt_head_bwd", "mt_prof_enable", "mt_prof_reset", "mt_prof_collect", "mt_prof_launch_count",
 ]
 
 vp, fp, i32, sz = C.c_void_p, C.c_void_p, C.c_int, C.c_size_t   # all device pointers travel as void*
@@ -117,6 +120,22 @@ def load() -> C.CDLL:
     lib.mt_head_fwd.argtypes = [fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, vp]
     lib.mt_aggregate_attn_fwd.argtypes = [fp, fp, fp, i32, i32, i32, i32, C.c_float, vp]
     lib.mt_clip_meta_fwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.mt_grad_prep_workspace_bytes.argtypes = [i32, i32]
+    lib.mt_grad_prep_workspace_bytes.restype = sz
+    lib.mt_grad_prep.argtypes = [i32, vp, i32, vp, vp, fp, i32, i32, i32, i32, vp, sz, vp]
+    lib.mt_colsum_f32.argtypes = [fp, fp, i32, i32, i32, vp]
+    lib.mt_layernorm_bwd_workspace_bytes.argtypes = [i32, i32]
+    lib.mt_layernorm_bwd_workspace_bytes.restype = sz
+    lib.mt_layernorm_bwd.argtypes = [i32, fp, fp, vp, fp, fp, i32, i32, vp, sz, vp]
+    lib.mt_geglu_fwd.argtypes = [i32, vp, vp, i32, i32, vp]
+    lib.mt_geglu_bwd.argtypes = [i32, vp, vp, vp, i32, i32, vp]
+    lib.mt_divided_attn_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.mt_divided_attn_bwd_workspace_bytes.restype = sz
+    lib.mt_divided_attn_bwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.mt_embed_bwd.argtypes = [fp, vp, vp, fp, fp, fp, i32, i32, i32, i32, vp]
+    lib.mt_head_bwd_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.mt_head_bwd_workspace_bytes.restype = sz
+    lib.mt_head_bwd.argtypes = [fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, vp, sz, vp]
     lib.mt_prof_enable.argtypes = [i32]
     lib.mt_prof_enable.restype = None
     lib.mt_prof_reset.restype = None
@@ -125,9 +144,9 @@ def load() -> C.CDLL:
     lib.mt_prof_launch_count.restype = C.c_ulonglong
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name.endswith("_fwd"):
+        if name.endswith(("_fwd", "_bwd")) or name in ("mt_grad_prep", "mt_colsum_f32"):
             fn.restype = i32
-    if lib.mt_abi_version() != 2:
+    if lib.mt_abi_version() != 3:
         raise RuntimeError("mintime_b200: ABI version mismatch between _lib.py and libmintime_b200.so")
     _lib = lib
     return lib

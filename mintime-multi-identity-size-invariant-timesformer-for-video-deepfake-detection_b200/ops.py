@@ -225,3 +225,137 @@ def head(x, ln_g, ln_b, w, bias):
                                      logits.data_ptr(), B, tokens, dim, classes, _lib.stream_ptr())
     _lib.check(rc, "mt_head_fwd")
     return logits
+
+
+# ---------------------------------------------------------------------------------------------------
+# Backward building blocks (csrc/train.cu; schedule in training.py)
+# ---------------------------------------------------------------------------------------------------
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def grad_prep(src, want_rm=False, want_t=False, want_colsum=False, rows_per_batch=0, m=None, precision="bf16"):
+    """One pass over src [rows, C] (float32 or T): -> (cast copy T [m, C] | None, transpose T [C, mp] | None with the
+    columns m..mp-1 zero, column sums float32 [C] | None).  rows_per_batch > 0 drops the CLS row of every video
+    (source row = i + i // rows_per_batch + 1; pass m = the number of kept rows)."""
+    T = _T(precision)
+    _prep(src)
+    if src.dtype not in (torch.float32, T):
+        raise TypeError(f"grad_prep: src must be float32 or {T}, got {src.dtype}")
+    rows, c = src.shape
+    m = rows if m is None else m
+    mp = round_up(m, 64)
+    dev = src.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    out_rm = torch.empty((m, c), dtype=T, device=dev) if want_rm else None
+    out_t = torch.empty((c, mp), dtype=T, device=dev) if want_t else None
+    cs = torch.empty((c,), dtype=torch.float32, device=dev) if want_colsum else None
+    ws_bytes = int(lib.mt_grad_prep_workspace_bytes(mp, c)) if want_colsum else 0
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mt_grad_prep(_lib.prec_id(precision), src.data_ptr(), int(src.dtype == torch.float32), _lib.ptr(out_rm),
+                              _lib.ptr(out_t), _lib.ptr(cs), m, c, mp, rows_per_batch, ws.data_ptr(), ws_bytes,
+                              _lib.stream_ptr())
+    _lib.check(rc, "mt_grad_prep")
+    return out_rm, out_t, cs
+
+
+def layernorm_bwd_(gx, x, gamma, dy, precision="bf16"):
+    """gx (float32 [rows, dim], in place) += LayerNorm backward of dy; returns (dgamma, dbeta)."""
+    _prep(x, torch.float32); _prep(gx, torch.float32); _prep(dy, _T(precision))
+    rows, dim = x.shape
+    dev = x.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    ws_bytes = int(lib.mt_layernorm_bwd_workspace_bytes(rows, dim))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    dgb = torch.empty((2 * dim,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mt_layernorm_bwd(_lib.prec_id(precision), x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), gx.data_ptr(),
+                                  dgb.data_ptr(), rows, dim, ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+    _lib.check(rc, "mt_layernorm_bwd")
+    return dgb[:dim], dgb[dim:]
+
+
+def geglu(h, precision="bf16"):
+    """h [m, 2*n_out] in the interleaved column order of the packed net.0 weight -> u * gelu(g)  [m, n_out]"""
+    T = _T(precision)
+    _prep(h, T)
+    m, n2 = h.shape
+    _lib.require_device(h.device)
+    out = torch.empty((m, n2 // 2), dtype=T, device=h.device)
+    with torch.cuda.device(h.device):
+        rc = _lib.load().mt_geglu_fwd(_lib.prec_id(precision), h.data_ptr(), out.data_ptr(), m, n2 // 2, _lib.stream_ptr())
+    _lib.check(rc, "mt_geglu_fwd")
+    return out
+
+
+def geglu_bwd(h, dout, precision="bf16"):
+    T = _T(precision)
+    _prep(h, T); _prep(dout, T)
+    m, n2 = h.shape
+    _lib.require_device(h.device)
+    dh = torch.empty_like(h)
+    with torch.cuda.device(h.device):
+        rc = _lib.load().mt_geglu_bwd(_lib.prec_id(precision), h.data_ptr(), dout.data_ptr(), dh.data_ptr(), m, n2 // 2,
+                                      _lib.stream_ptr())
+    _lib.check(rc, "mt_geglu_bwd")
+    return dh
+
+
+def divided_attention_bwd(qkv, dout, mask_u8, idmask_u8, mode: str, f: int, n: int, heads: int, dim_head: int = 64,
+                          precision="bf16"):
+    """Backward of divided_attention: (qkv, d out) -> d qkv, same shape as qkv."""
+    T = _T(precision)
+    _prep(qkv, T); _prep(dout, T)
+    B, N, _ = qkv.shape
+    dev = qkv.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    dqkv = torch.empty_like(qkv)
+    ws_bytes = int(lib.mt_divided_attn_bwd_workspace_bytes(B, f, n, heads))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mt_divided_attn_bwd(_lib.prec_id(precision), qkv.data_ptr(), dout.data_ptr(), mask_u8.data_ptr(),
+                                     _lib.ptr(idmask_u8), _lib.ATTN_TIME if mode == "time" else _lib.ATTN_SPACE,
+                                     dqkv.data_ptr(), B, f, n, heads, dim_head, ws.data_ptr(), ws_bytes,
+                                     _lib.stream_ptr())
+    _lib.check(rc, "mt_divided_attn_bwd")
+    return dqkv
+
+
+def embed_bwd(g0, positions, size_embedding, table_rows: int, f: int, n: int, want_pos=True, want_size=True):
+    """g0 float32 [B, 1+f*n, dim] -> (d pos_emb.weight | None, d size_emb.weight | None, d cls_token [dim])"""
+    _prep(g0, torch.float32)
+    B, N, dim = g0.shape
+    dev = g0.device
+    _lib.require_device(dev)
+    dpos = torch.zeros((table_rows, dim), dtype=torch.float32, device=dev) if want_pos else None
+    dsize = torch.zeros((table_rows, dim), dtype=torch.float32, device=dev) if want_size else None
+    dcls = torch.zeros((dim,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().mt_embed_bwd(g0.data_ptr(), _lib.ptr(positions), _lib.ptr(size_embedding), _lib.ptr(dpos),
+                                      _lib.ptr(dsize), dcls.data_ptr(), B, f, n, dim, _lib.stream_ptr())
+    _lib.check(rc, "mt_embed_bwd")
+    return dpos, dsize, dcls
+
+
+def head_bwd_(gx, x, ln_g, ln_b, w, dlogits):
+    """gx[:, 0, :] = d x[:, 0] (assigned); returns (dW [classes, dim], dbias [classes], dgamma [dim], dbeta [dim])"""
+    _prep(x, torch.float32); _prep(gx, torch.float32); _prep(dlogits, torch.float32)
+    B, tokens, dim = x.shape
+    classes = w.shape[0]
+    dev = x.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    ws_bytes = int(lib.mt_head_bwd_workspace_bytes(B, dim, classes))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    grads = torch.empty((classes * dim + classes + 2 * dim,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mt_head_bwd(x.data_ptr(), ln_g.data_ptr(), ln_b.data_ptr(), w.data_ptr(), dlogits.data_ptr(),
+                             gx.data_ptr(), grads.data_ptr(), B, tokens, dim, classes, ws.data_ptr(), ws_bytes,
+                             _lib.stream_ptr())
+    _lib.check(rc, "mt_head_bwd")
+    o = classes * dim
+    return grads[:o].view(classes, dim), grads[o:o + classes], grads[o + classes:o + classes + dim], grads[o + classes + dim:]

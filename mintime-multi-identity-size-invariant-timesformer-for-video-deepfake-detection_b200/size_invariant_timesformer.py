@@ -3,7 +3,9 @@
 Same constructor (``config=dict`` with the hyphenated yaml keys, ``require_attention``), same
 ``forward(x, mask=, identities_mask=, size_embedding=, positions=)`` and return values, same
 ``state_dict`` names/shapes and initialisation (:148-214).  The sub-modules only hold parameters;
-the forward is one call into libmintime_b200.so (mt_tsf_fwd).  There is no PyTorch fallback.
+the forward is one call into libmintime_b200.so (mt_tsf_fwd).  When gradients are enabled and a parameter requires
+them (train.py:332-378) the forward/backward schedule of ``training.py`` runs instead, as one autograd node, so
+``loss.backward()`` fills ``param.grad`` from the library's backward kernels.  There is no PyTorch fallback.
 """
 from __future__ import annotations
 
@@ -77,7 +79,8 @@ class SizeInvariantTimeSformer(nn.Module):
             raise NotImplementedError("shift-tokens: True is broken in the reference (NameError at "
                                       "size_invariant_timesformer.py:189) and not supported")
         if self.attn_dropout or self.ff_dropout:
-            raise NotImplementedError("dropout > 0 is not supported on the inference path")
+            # (the shipped config/size_invariant_timesformer.yaml has attn-dropout = ff-dropout = 0)
+            raise NotImplementedError("dropout > 0 is not supported")
 
         num_positions = self.num_frames * self.channels                        # :173
         self.to_patch_embedding = nn.Linear(self.channels, self.dim)
@@ -103,6 +106,8 @@ class SizeInvariantTimeSformer(nn.Module):
         self._packed_key = None
         self._cfg_struct = weights.tsf_cfg_struct(config)
         self._ws = None
+        self._train_pack = None
+        self._train_pack_key = None
 
     def _init_weights(self, m):                                                # :207-214
         if isinstance(m, nn.Linear):
@@ -138,6 +143,15 @@ class SizeInvariantTimeSformer(nn.Module):
             self._packed = weights.pack_tsf(self.state_dict(), self.config, self.precision, device)
             self._packed_key = key
         return self._packed
+
+    def _get_train_pack(self, device):
+        from . import training
+        key = (self.precision, str(device), tuple(p._version for p in self.parameters()),
+               tuple(p.data_ptr() for p in self.parameters()))
+        if self._train_pack is None or self._train_pack_key != key:
+            self._train_pack = training.TrainPack(self, self.precision, device)
+            self._train_pack_key = key
+        return self._train_pack
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, mask=None, identities_mask=None, size_embedding=None, positions=None):
@@ -190,6 +204,17 @@ class SizeInvariantTimeSformer(nn.Module):
             if pos.shape != (b, 1 + f * n):
                 raise ValueError(f"positions must be (B,1+f*n), got {tuple(pos.shape)}")
         N = 1 + f * n
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step (train.py:355, 376-378): forward that keeps activations + hand-written backward
+            from . import training
+            if x.requires_grad:
+                raise NotImplementedError("gradients w.r.t. the input features (an unfrozen extractor, train.py:155-170) "
+                                          "are not produced; run the extractor under no_grad (--freeze_backbone)")
+            out = training.TsfTrainFunction.apply(self, tok.reshape(b, f * n, c), mask_u8, idm_u8, se, pos,
+                                                  *self.parameters())
+            if self.require_attention:
+                return out[0], [out[1], out[2]]
+            return out
         with torch.cuda.device(dev):
             pk = self._get_packed(dev)
             need = lib.mt_tsf_workspace_bytes(self._cfg_struct, b, prec)

@@ -58,3 +58,26 @@ def rel_err(a, b):
     a = torch.as_tensor(a).double().flatten()
     b = torch.as_tensor(b).double().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------
+# training-step cases (oracle/make_golden_grads.py): name -> (B, f, identities, depth)
+# ---------------------------------------------------------------------------------------------------
+GRAD_CASES = {
+    "b2_f8_id2": (2, 8, [2, 1], 9),
+    "b3_f16_mixed_d2": (3, 16, [3, 1, 2], 2),
+}
+
+
+def grad_case_inputs(name):
+    """(cfg, tsf_sd, meta, feats (B,f,1280,7,7) bf16-representable float32, labels (B,1), pos_weight)"""
+    B, f, ids, depth = GRAD_CASES[name]
+    cfg = default_tsf_config(num_frames=f, channels=1280)
+    cfg["model"]["depth"] = depth
+    tsd = synth.make_tsf_state_dict(cfg, 777)
+    meta = synth.make_batch_meta(B, f, ids, seed=f + 1, pad_tail=True)
+    g = torch.Generator().manual_seed(1000 + f)
+    feats = torch.nn.functional.silu(torch.randn((B, f, 1280, 7, 7), generator=g)) * 20.0
+    feats = feats.bfloat16().float()
+    labels = torch.tensor([[float(i % 2 == 0)] for i in range(B)])
+    return cfg, tsd, meta, feats, labels, 0.8169

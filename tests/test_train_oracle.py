@@ -1,0 +1,53 @@
+"""CPU: the oracle's gradients (torch autograd through oracle/mintime_oracle.py) against the gradients of the UNMODIFIED
+reference stored in tests/golden/grads_*.npz (oracle/make_golden_grads.py), and the host-side training helpers."""
+import numpy as np
+import pytest
+import torch
+
+import mintime_b200  # noqa: F401
+from mintime_b200 import training, weights
+from oracle import mintime_oracle as orc
+from helpers import GRAD_CASES, grad_case_inputs, load_golden, sample
+
+
+@pytest.mark.parametrize("case", list(GRAD_CASES))
+def test_oracle_autograd_matches_reference_gradients(case):
+    cfg, tsd, meta, feats, labels, pw = grad_case_inputs(case)
+    gold = load_golden("grads_" + case)
+    sd = {k: v.clone().requires_grad_(True) for k, v in tsd.items()}
+    logits, _ = orc.tsf_forward(sd, cfg, feats, meta["mask"], meta["identities_mask"], meta["size_embedding"],
+                                meta["positions"])
+    loss = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw]))(logits, labels)
+    loss.backward()
+    assert np.allclose(logits.detach().numpy(), gold["logits"], rtol=1e-4, atol=1e-5)
+    assert abs(loss.item() - float(gold["loss"])) <= 1e-6
+    checked = 0
+    for k, v in sd.items():
+        if f"grad.{k}.sample" not in gold:
+            continue
+        ref = gold[f"grad.{k}.sample"]
+        got = sample(v.grad, 512)
+        assert np.linalg.norm(got - ref) <= 1e-4 * np.linalg.norm(ref) + 1e-10, k
+        assert abs(float(v.grad.double().norm()) - float(gold[f"grad.{k}.norm"])) <= 1e-4 * float(gold[f"grad.{k}.norm"]) + 1e-10
+        checked += 1
+    assert checked == len([k for k in gold if k.endswith(".norm")])
+
+
+def test_geglu_uninterleave_inverts_interleave():
+    t = torch.arange(256 * 3, dtype=torch.float32).view(256, 3)
+    assert torch.equal(training._uninterleave(weights.geglu_interleave(t)), t)
+    b = torch.arange(128, dtype=torch.float32)
+    assert torch.equal(training._uninterleave(weights.geglu_interleave(b)), b)
+
+
+def test_layer_gradient_layout_covers_every_layer_parameter():
+    from mintime_b200 import SizeInvariantTimeSformer
+    from mintime_b200.spec import default_tsf_config
+    cfg = default_tsf_config(num_frames=8)
+    cfg["model"]["depth"] = 1
+    model = SizeInvariantTimeSformer(config=cfg)
+    dim, inner = 512, 512
+    names = {f"layers.0.{j}.{k}": s for j, lay in ((0, training._attn_layout(dim, inner)), (1, training._attn_layout(dim, inner)),
+                                                  (2, training._ff_layout(dim))) for k, s in lay}
+    got = {k: tuple(p.shape) for k, p in model.named_parameters() if k.startswith("layers.0.")}
+    assert names == got
