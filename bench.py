@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attention-maps", action="store_true", help="also return the CLS attention maps (config 5)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE configs[1] (default, the metric's config); train: configs[3], the train.py step")
     ap.add_argument("--no-graph", action="store_true",
                     help="call the nn.Modules eagerly instead of replaying the step as a CUDA graph (GraphedHotPath)")
     args = ap.parse_args()
@@ -183,6 +185,10 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, emit)
+        return
+    if args.mode == "train":
+        from bench_train import run_train
+        run_train(args, emit, ClockSampler, load_peaks)
         return
 
     import mintime_b200

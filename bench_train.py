@@ -1,0 +1,187 @@
+"""`python bench.py --mode train` -- BASELINE.json configs[3]: the training step of train.py:332-378 (frozen extractor:
+--freeze_backbone) on synthetic ForgeryNet-shaped clips, bf16 compute / fp32 master weights, SGD(lr 0.01, wd 1e-4),
+BCEWithLogits(pos_weight); one process per GPU, gradients averaged by the per-layer all-reduce issued from inside the
+backward (mintime_b200.training.GradSync, NCCL).  Same JSON contract as the inference line of bench.py; a step =
+H2D of the uint8 clips + extractor forward + transformer forward/backward + optimizer step + loss D2H."""
+import json
+import os
+import time
+
+import torch
+
+
+def cpu_train_videos_per_sec(batch, frames, identities, steps=2):
+    """The oracle's training step (extractor forward under no_grad + autograd through the transformer + SGD) on the host."""
+    from mintime_b200 import synth
+    from mintime_b200.spec import default_tsf_config
+    from oracle import mintime_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    cfg = default_tsf_config(num_frames=frames)
+    esd = synth.make_effnet_state_dict(1234)
+    tsd = {k: v.clone().requires_grad_(True) for k, v in synth.make_tsf_state_dict(cfg, 4321).items()}
+    opt = torch.optim.SGD(list(tsd.values()), lr=0.01, weight_decay=1e-4)
+    meta = synth.make_batch_meta(batch, frames, identities, seed=1234)
+    clip = synth.make_frames(batch, frames, seed=1234, mask=meta["mask"])
+    labels = (torch.arange(batch) % 2).float().view(batch, 1)
+    lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([0.8169]))
+
+    def step():
+        with torch.no_grad():
+            feats = orc.effnet_b0_forward(esd, clip.view(batch * frames, 224, 224, 3).permute(0, 3, 1, 2))
+        feats = feats.view(batch, frames, *feats.shape[1:])
+        opt.zero_grad()
+        logits, _ = orc.tsf_forward(tsd, cfg, feats, meta["mask"], meta["identities_mask"], meta["size_embedding"],
+                                    meta["positions"])
+        lossf(logits, labels).backward()
+        opt.step()
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    sec = (time.perf_counter() - t0) / steps
+    return batch / sec, sec, torch.get_num_threads()
+
+
+def run_train(args, emit, ClockSampler, load_peaks):
+    import mintime_b200
+    from mintime_b200 import _lib, synth, training
+    from mintime_b200 import dist as mdist
+    from mintime_b200.spec import default_tsf_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --mode train needs a GPU (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, f = args.batch, args.frames
+    cfg = default_tsf_config(num_frames=f)
+    ext = mintime_b200.EfficientNet.from_name("efficientnet-b0", precision=args.precision)
+    ext.load_state_dict(synth.make_effnet_state_dict(1234))
+    ext = ext.to(dev).eval()                                            # train.py:153-154 (freeze_backbone)
+    model = mintime_b200.SizeInvariantTimeSformer(config=cfg, precision=args.precision)
+    model.load_state_dict(synth.make_tsf_state_dict(cfg, 4321))
+    model = model.to(dev).train()                                       # train.py:315
+    if world > 1:
+        training.attach_grad_sync(model)
+    opt = torch.optim.SGD(model.parameters(), lr=cfg["training"]["lr"], weight_decay=cfg["training"]["weight-decay"])
+    lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([0.8169], device=dev))
+
+    meta = synth.make_batch_meta(B, f, args.identities, seed=1234 + rank)
+    host = {"clip": synth.make_frames(B, f, seed=1234 + rank, mask=meta["mask"], dtype=torch.uint8).pin_memory(),
+            "labels": (torch.rand((B, 1), generator=torch.Generator().manual_seed(rank)) < 0.55).float().pin_memory(),
+            **{k: v.pin_memory() for k, v in meta.items()}}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def train_step(m):
+        with torch.no_grad():                                           # train.py:344-346
+            feats = ext(m["clip"].view(B * f, 224, 224, 3).permute(0, 3, 1, 2)).reshape(B, f, 1280, 7, 7)
+        opt.zero_grad(set_to_none=True)
+        y = model(feats, mask=m["mask"], size_embedding=m["size_embedding"], identities_mask=m["identities_mask"],
+                  positions=m["positions"])
+        loss = lossf(y, m["labels"])
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_resident():
+        return train_step(resident)
+
+    def step_e2e():
+        m = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss_host.copy_(train_step(m).detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return loss_host
+
+    def barrier():
+        mdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        barrier()
+        return mdist.max_over_ranks(ms, device=dev)
+
+    lib = _lib.load()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    launches0 = lib.mt_prof_launch_count()
+    ms = timed(step_resident, args.steps, 0)
+    launches = lib.mt_prof_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    lib.mt_prof_reset()
+    lib.mt_prof_enable(1)
+    step_resident()
+    torch.cuda.synchronize()
+    lib.mt_prof_enable(0)
+    prof = _lib.profile_collect()
+    lib.mt_prof_reset()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_train_videos_per_sec(2, f, args.identities)
+        cpu = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port",
+               "sample": f"2 clips x {f} frames per training step (oracle: extractor forward + torch autograd through the "
+                         f"fp32 restatement + SGD), 2 timed steps after 1 warm-up, {sec:.2f} s/step"}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    ridge = peaks["tensor"] * 1e12 / (peaks["hbm"] * 1e9)
+    total_ms = sum(p[1] for p in prof) or 1.0
+    kernels = []
+    for name, ms_t, fl, by, cnt in prof:
+        sec = ms_t * 1e-3
+        bound = "tensor" if (by > 0 and fl / by >= ridge and name.startswith("gemm")) else "hbm"
+        ach = fl / sec / 1e12 if bound == "tensor" else by / sec / 1e9
+        peak = peaks["tensor"] if bound == "tensor" else peaks["hbm"]
+        kernels.append({"name": name, "share": ms_t / total_ms, "ms_per_launch": ms_t / cnt, "launches_per_step": cnt,
+                        "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                        "frac": ach / peak})
+    dom = kernels[0] if kernels else None
+    roofline = None
+    if dom:
+        roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": None, "kernel": dom["name"], "share_of_step": dom["share"],
+                    "ms_per_launch": dom["ms_per_launch"], "peak_source": peaks["source"]}
+    h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
+    emit({
+        "metric": "train_videos_per_sec_16f_224px", "value": world * B / (ms * 1e-3), "unit": "videos/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[3]: train.py step, frozen EfficientNet-B0 (eval, no_grad) -> "
+                               "SizeInvariantTimeSformer forward + backward + SGD, synthetic ForgeryNet-shaped clips",
+                   "batch_per_gpu": B, "frames": f, "identities": ",".join(map(str, args.identities)),
+                   "precision": args.precision + " compute, fp32 master weights and gradients",
+                   "grad_exchange": "per-layer flat buckets, all-reduce issued inside the backward (NCCL)" if world > 1 else "none (1 GPU)",
+                   "timing": "CUDA events on the launch stream, max over ranks; activations per step (6.7 GB) exceed the L2"},
+        "clocks": clocks,
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e, "input": "uint8 NHWC clips, masks, positions, labels from pinned host memory every "
+                                                "step; loss D2H + stream sync every step"},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels[:24],
+        "sum_kernel_ms_per_step": total_ms,
+    })

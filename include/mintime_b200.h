@@ -252,6 +252,12 @@ size_t mt_grad_prep_workspace_bytes(int m, int c);
 int mt_grad_prep(int precision, const void* src, int src_is_f32, void* out_rm, void* out_t, float* colsum, int m, int c,
                  int mp, int rows_per_batch, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight gradient of a Linear: dw f32 [n_out][k_in] += dy_t [n_out][mp] * x_t [k_in][mp]^T  (both operands T, from
+ * mt_grad_prep; contraction over the mp tokens).  Same GEMM as mt_linear_residual_fwd with the k-blocks of every
+ * output tile split over the SMs (partial tiles are summed by the TMA reduce-add of the epilogue, so the summation order
+ * of the fp32 partials is not fixed). */
+int mt_linear_wgrad(int precision, const void* dy_t, const void* x_t, float* dw, int n_out, int k_in, int mp, void* stream);
+
 /* out[c] (+)= sum_r in[r][c], fixed summation order. */
 int mt_colsum_f32(const float* in, float* out, int rows, int cols, int accumulate, void* stream);
 

@@ -136,6 +136,7 @@ struct GemmArgs {
   const float* gate;  // f32 [M / rows_per_gate][K] or null
   int rows_per_gate;
   EpiParams epi;
+  int splits;         // > 1: split-K request (honoured for EPI_RESID_F32 without bias on the tensor-core path)
 };
 
 // One group of 8 consecutive output columns [col, col+8) of row `row` (both already bounds-checked).

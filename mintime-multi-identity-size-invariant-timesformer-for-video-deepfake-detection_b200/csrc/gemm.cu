@@ -42,6 +42,8 @@ struct TcParams {
   int acc_stages;   // TMEM accumulator buffers (2, or 1 when two CTAs share the SM's 512 columns at block_n > 128)
   int gate_imgs;    // > 0: SE gate rows of up to this many images are staged in smem per tile (GATED)
   int b_resident;   // 1: the whole weight matrix (one column tile, all k-blocks) is loaded into smem once per block
+  int splits;       // split-K (EPI_RESID_F32 through the TMA reduce-add only): every output tile is worked on by
+  int kb_per_split; // `splits` tiles, each over kb_per_split k-blocks; the cp.reduce .add epilogue sums them in L2
   const float* gate;
   int rows_per_gate;
   EpiParams epi;
@@ -177,7 +179,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int mn_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = mn_tiles * p.splits;      // tile = split * mn_tiles + (m-tile, n-tile)
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -193,9 +196,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       const uint32_t tx_bytes = (uint32_t)(kAStageBytes + (p.b_resident ? 0 : b_stage_bytes));
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * kBlockM;
-        const int n0 = (tile % p.tiles_n) * p.block_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = tile / mn_tiles, t2 = tile - split * mn_tiles;
+        const int m0 = (t2 / p.tiles_n) * kBlockM;
+        const int n0 = (t2 % p.tiles_n) * p.block_n;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
           ptx::tma_load_2d(smem_a + ps.stage * kAStageBytes, &tmap_a, &full_bar[ps.stage], kb * kBlockK, m0);
@@ -219,7 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * p.block_n);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (tile / mn_tiles) * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(GATED ? &gated_bar[ps.stage] : &full_bar[ps.stage], ps.phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem_a + ps.stage * kAStageBytes);
@@ -229,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * 32);
             const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * 32);
-            ptx::umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[ps.stage]);  // smem slot free once these MMAs retire
           ps.advance(p.stages);
@@ -259,8 +265,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int as = p.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
       if (p.acc_stages == 2 && as != half) continue;
-      const int m0 = (tile / p.tiles_n) * kBlockM;
-      const int n0 = (tile % p.tiles_n) * p.block_n;
+      const int t2 = tile % mn_tiles;
+      const int m0 = (t2 / p.tiles_n) * kBlockM;
+      const int n0 = (t2 % p.tiles_n) * p.block_n;
       const int row = m0 + trow;
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
@@ -338,8 +345,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = p.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
-      const int m0 = (tile / p.tiles_n) * kBlockM;
-      const int n0 = (tile % p.tiles_n) * p.block_n;
+      const int t2 = tile % mn_tiles;
+      const int m0 = (t2 / p.tiles_n) * kBlockM;
+      const int n0 = (t2 % p.tiles_n) * p.block_n;
       const int row = m0 + trow;
       const bool row_ok = row < p.M;
       ptx::mbar_wait(&tmem_full[as], aphase);
@@ -476,7 +484,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int r = threadIdx.x - kGateThread0;  // tile row 0..127
     PipeState ps;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * kBlockM;
+      const int m0 = ((tile % mn_tiles) / p.tiles_n) * kBlockM;
       const int row = m0 + r;
       const int img = (row < p.M ? row : p.M - 1) / p.rows_per_gate;
       const float* grow = p.gate + (size_t)img * p.K;   // global row (fallback when the gates are not staged)
@@ -734,6 +742,15 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   const int num_kb = (g.K + kBlockK - 1) / kBlockK;
   const int b_block = bn * kBlockK * 2;
   p.b_resident = (p.tiles_n == 1 && num_kb * b_block <= 40 * 1024) ? 1 : 0;
+  // split-K: only where partial tiles can be summed by the epilogue itself (fp32 TMA reduce-add, no bias)
+  p.splits = 1;
+  p.kb_per_split = num_kb;
+  if (KIND == EPI_RESID_F32 && TMA_OUT && !GATED && g.splits > 1 && !g.epi.bias && !p.b_resident) {
+    int kbs = (num_kb + g.splits - 1) / g.splits;
+    if (kbs < 8) kbs = 8;
+    p.kb_per_split = kbs;
+    p.splits = (num_kb + kbs - 1) / kbs;           // every split owns at least one k-block
+  }
   const int stage_bytes = kAStageBytes + (p.b_resident ? 0 : b_block);
   const int bias_bytes = kEW == 8 ? ((g.N * 4 + 15) & ~15) : 0;
   // SE gates staged per tile: a 128-row tile touches at most (127 / rows_per_gate) + 2 images
@@ -783,7 +800,7 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc)");
     attr_set = true;
   }
-  int grid = p.tiles_m * p.tiles_n;
+  int grid = p.tiles_m * p.tiles_n * p.splits;
   if (grid > num_sms() * ctas_per_sm) grid = num_sms() * ctas_per_sm;
   kern<<<grid, tc_threads<KIND, GATED, TMA_OUT>(), smem, stream>>>(ta, tb, tout, p);
   MT_LAUNCH_CHECK("gemm_tc_kernel");
@@ -805,7 +822,7 @@ template <int KIND, bool GATED>
 int launch_tc(const GemmArgs& g, cudaStream_t stream) {
   if constexpr (!GATED && (KIND == EPI_STORE || KIND == EPI_GEGLU || KIND == EPI_RESID_F32)) {
     // large transformer contractions: CTA-pair kernel (256x256 tiles, cta_group::2)
-    if (tc2_enabled() && tc2_eligible(g)) return launch_tc2<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
+    if (tc2_enabled() && g.splits <= 1 && tc2_eligible(g)) return launch_tc2<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
   }
   // per-row gathers (skip connection, embedding rows) use the direct epilogue; everything else TMA
   if (KIND == EPI_PATCH_EMBED) return launch_tc_impl<KIND, GATED, false>(g, stream);

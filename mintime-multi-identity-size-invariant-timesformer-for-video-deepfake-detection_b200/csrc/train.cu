@@ -12,9 +12,12 @@
 // like torch's own embedding backward.
 #include <float.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
+#include "attention_bwd_mma.cuh"
 #include "common.cuh"
 
 namespace mt {
@@ -183,30 +186,42 @@ int launch_ln_bwd(const float* x, const float* gamma, const void* dy, float* gx,
 // rows_per_batch > 0 drops the CLS row of every video: source row = m + m / rows_per_batch + 1 (patch-embedding wgrad).
 // 64 x 64 tiles, 256 threads.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 load2f(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load2f(const bf16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ void store2f(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2f(bf16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+// Each thread moves element pairs: 128-byte (bf16) / 256-byte (f32) row segments per warp on the way in, 128-byte
+// segments of the transposed rows on the way out.
 template <typename TIn, typename T>
 __global__ void __launch_bounds__(256) grad_prep_kernel(const TIn* __restrict__ src, T* __restrict__ out_rm,
                                                         T* __restrict__ out_t, float* __restrict__ colpart, int M, int C,
                                                         int Mp, int rows_per_batch) {
   __shared__ float tile[64][65];
   const int c0 = blockIdx.x * 64, m0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    const int mm = i * 4 + ty, m = m0 + mm;
-    float v = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const int mm = i * 8 + ty, m = m0 + mm;
+    float2 v = make_float2(0.f, 0.f);
     if (m < M) {
       const size_t srow = rows_per_batch ? (size_t)m + m / rows_per_batch + 1 : (size_t)m;
-      v = to_f(src[srow * C + c0 + tx]);
-      if (out_rm) out_rm[(size_t)m * C + c0 + tx] = from_f<T>(v);
+      v = load2f(src + srow * C + c0 + tx * 2);
+      if (out_rm) store2f(out_rm + (size_t)m * C + c0 + tx * 2, v.x, v.y);
     }
-    tile[mm][tx] = v;
+    tile[mm][tx * 2] = v.x;
+    tile[mm][tx * 2 + 1] = v.y;
   }
   __syncthreads();
   if (out_t) {
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int cc = i * 4 + ty;
-      out_t[(size_t)(c0 + cc) * Mp + m0 + tx] = from_f<T>(tile[tx][cc]);
+    for (int i = 0; i < 8; ++i) {
+      const int cc = i * 8 + ty;
+      store2f(out_t + (size_t)(c0 + cc) * Mp + m0 + tx * 2, tile[tx * 2][cc], tile[tx * 2 + 1][cc]);
     }
   }
   if (colpart && threadIdx.x < 64) {
@@ -554,7 +569,21 @@ int launch_attn_bwd(const void* qkv_, const void* dout_, const uint8_t* mask, co
     ProfScope prof(st, 10.0 * B * heads * G * 64.0 * Gq * Gk, (double)B * N * heads * 64 * (7.0 * sizeof(T) + 512.0),
                    mode == MT_ATTN_TIME ? "attn_time_bwd" : "attn_space_bwd");
     const size_t smem = (size_t)(2 * Gk * 65 + 2 * Gq * 65 + 2 * Gq * 64) * sizeof(float);
-    if (mode == MT_ATTN_TIME) {
+    int rc_mma = MT_ERR_UNSUPPORTED;
+    if constexpr (std::is_same<T, bf16>::value) {
+      // bf16 path: warp-level tensor-core kernel (attention_bwd_mma.cuh); MINTIME_B200_ATTN_BWD=simt keeps the FFMA one
+      static int use_mma = -1;
+      if (use_mma < 0) {
+        const char* e = getenv("MINTIME_B200_ATTN_BWD");
+        use_mma = (e && e[0] == 's') ? 0 : 1;
+      }
+      if (use_mma)
+        rc_mma = attn::launch_attn_group_bwd_mma(mode, qkv, dout, mask, idmask, dqkv, ws_kv, ws_cls, B, f, n, heads, st);
+      if (rc_mma != MT_OK && rc_mma != MT_ERR_UNSUPPORTED) return rc_mma;
+    }
+    if (rc_mma == MT_OK) {
+      // (launched above)
+    } else if (mode == MT_ATTN_TIME) {
       auto kern = attn_group_bwd_kernel<T, MT_ATTN_TIME>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
       if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(attn_time_bwd)");
@@ -565,7 +594,7 @@ int launch_attn_bwd(const void* qkv_, const void* dout_, const uint8_t* mask, co
       if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(attn_space_bwd)");
       kern<<<B * heads * G, 128, smem, st>>>(qkv, dout, mask, idmask, dqkv, ws_kv, ws_cls, f, n, heads);
     }
-    MT_LAUNCH_CHECK("attn_group_bwd_kernel");
+    if (rc_mma != MT_OK) MT_LAUNCH_CHECK("attn_group_bwd_kernel");
   }
   attn_cls_finish_kernel<T><<<B * heads, 64, 0, st>>>(dqkv, ws_kv, ws_q, ws_cls, N, G, heads);
   MT_LAUNCH_CHECK("attn_cls_finish_kernel");
@@ -662,6 +691,18 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
 }  // namespace mt
 
 using namespace mt;
+
+extern "C" int mt_linear_wgrad(int precision, const void* dy_t, const void* x_t, float* dw, int n_out, int k_in, int mp,
+                               void* stream) {
+  MT_REQUIRE(dy_t && x_t && dw && n_out > 0 && k_in > 0 && mp > 0, "linear_wgrad: bad argument");
+  GemmArgs g{};
+  g.a = dy_t; g.w = x_t; g.M = n_out; g.N = k_in; g.K = mp;
+  g.epi.kind = EPI_RESID_F32; g.epi.M = n_out; g.epi.N = k_in; g.epi.bias = nullptr; g.epi.out = dw; g.epi.ldo = k_in;
+  // few output tiles, a very long contraction: spread the k-blocks of every tile over the SMs
+  const int tiles = ((n_out + 127) / 128) * ((k_in + 255) / 256);
+  g.splits = std::max(1, (sm_count() + tiles / 2) / tiles);
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int mt_colsum_f32(const float* in, float* out, int rows, int cols, int accumulate, void* stream) {
   MT_REQUIRE(in && out && rows > 0 && cols > 0, "colsum: bad argument");

@@ -359,3 +359,19 @@ def head_bwd_(gx, x, ln_g, ln_b, w, dlogits):
     _lib.check(rc, "mt_head_bwd")
     o = classes * dim
     return grads[:o].view(classes, dim), grads[o:o + classes], grads[o + classes:o + classes + dim], grads[o + classes + dim:]
+
+
+def linear_wgrad_(dw, dy_t, x_t, precision="bf16"):
+    """dw (float32 [n_out, k_in], in place) += dy_t [n_out, mp] @ x_t [k_in, mp].T   (split-K tensor-core GEMM)"""
+    T = _T(precision)
+    _prep(dy_t, T); _prep(x_t, T); _prep(dw, torch.float32)
+    n_out, mp = dy_t.shape
+    k_in = x_t.shape[0]
+    if x_t.shape[1] != mp or tuple(dw.shape) != (n_out, k_in):
+        raise ValueError("linear_wgrad_: shape mismatch")
+    _lib.require_device(dw.device)
+    with torch.cuda.device(dw.device):
+        rc = _lib.load().mt_linear_wgrad(_lib.prec_id(precision), dy_t.data_ptr(), x_t.data_ptr(), dw.data_ptr(), n_out, k_in,
+                                         mp, _lib.stream_ptr())
+    _lib.check(rc, "mt_linear_wgrad")
+    return dw

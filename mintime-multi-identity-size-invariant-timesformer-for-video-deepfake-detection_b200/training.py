@@ -215,8 +215,33 @@ class TsfTrainFunction(torch.autograd.Function):
         grads["to_out.0.weight"], grads["to_out.0.bias"] = dgam, dbet
         g = g.view(M, dim)
 
-        def wgrad(dst, dyT, xT):
-            ops.linear_residual_(dst, dyT, xT, None, precision)
+        # The weight-gradient GEMMs have few output tiles (512 x 512 .. 4096 x 512 over a 25 k-long contraction) and
+        # nothing on the critical path reads them: they run on side streams, next to the main stream's kernels, and
+        # their post-processing (q-row scale, GEGLU row order) follows them on the same side stream.
+        main = torch.cuda.current_stream(dev)
+        side = _side_streams(model, dev)
+        turn = [0]
+
+        def wgrad(dst, dyT, xT, after=None):
+            s_ = side[turn[0] % len(side)]
+            turn[0] += 1
+            s_.wait_stream(main)
+            with torch.cuda.stream(s_):
+                ops.linear_wgrad_(dst, dyT, xT, precision)
+                if after is not None:
+                    after()
+            for t in (dst, dyT, xT):
+                t.record_stream(s_)
+
+        def side_done():
+            evs = []
+            for s_ in side:
+                e = torch.cuda.Event()
+                e.record(s_)
+                evs.append(e)
+            return evs
+
+        prev = None          # (flat buffer, side-stream events) of the layer processed before the current one
 
         attn_lay, ff_lay = _attn_layout(dim, inner), _ff_layout(dim)
         layer_numel = 2 * sum(_numel(s) for _, s in attn_lay) + sum(_numel(s) for _, s in ff_lay)
@@ -240,8 +265,7 @@ class TsfTrainFunction(torch.autograd.Function):
             _, dhT, cs = ops.grad_prep(dh_, want_t=True, want_colsum=True, precision=precision)
             _, xnT, _ = ops.grad_prep(xn, want_t=True, precision=precision)
             dw1 = torch.zeros((8 * dim, dim), dtype=f32, device=dev)      # interleaved row order of the packed weight
-            wgrad(dw1, dhT, xnT)
-            G["2.fn.net.0.weight"].copy_(_uninterleave(dw1))
+            wgrad(dw1, dhT, xnT, after=lambda dw1=dw1, dst=G["2.fn.net.0.weight"]: dst.copy_(_uninterleave(dw1)))
             G["2.fn.net.0.bias"].copy_(_uninterleave(cs))
             dxn = ops.pointwise(dh_, L["ff.w1_t"], precision=precision)
             del dh_, dhT, xnT, dw1
@@ -262,8 +286,8 @@ class TsfTrainFunction(torch.autograd.Function):
                 _, dqkvT, _ = ops.grad_prep(dqkv, want_t=True, precision=precision)
                 _, xnT, _ = ops.grad_prep(xn, want_t=True, precision=precision)
                 wq = G[f"{j}.fn.to_qkv.weight"]
-                wgrad(wq, dqkvT, xnT)
-                wq[:inner].mul_(scale)               # the packed q rows carry dim_head^-0.5 (:114)
+                # (the packed q rows carry dim_head^-0.5, :114)
+                wgrad(wq, dqkvT, xnT, after=lambda wq=wq: wq[:inner].mul_(scale))
                 dxn = ops.pointwise(dqkv, L[name + ".wqkv_t"], precision=precision)
                 del dqkv, dqkvT, xnT
                 dgm, dbt = ops.layernorm_bwd_(g, x_in, L[name + ".ln_g"], dxn, precision)
@@ -271,7 +295,12 @@ class TsfTrainFunction(torch.autograd.Function):
                 G[f"{j}.norm.bias"].copy_(dbt)
             ctx.saved[l] = None                      # release this layer's activations
             if sync is not None:
-                sync.launch(flat)
+                # the exchange of the PREVIOUS layer's bucket is issued now: its side-stream GEMMs have long finished
+                if prev is not None:
+                    for e in prev[1]:
+                        main.wait_event(e)
+                    sync.launch(prev[0])
+                prev = (flat, side_done())
             for k, v in G.items():
                 grads[f"layers.{l}.{k}"] = v
         # ---- token build (:225-248)
@@ -284,6 +313,10 @@ class TsfTrainFunction(torch.autograd.Function):
         _, tokT, _ = ops.grad_prep(tok.view(Mt, -1), want_t=True, precision=precision)
         dwp = torch.zeros((dim, model.channels), dtype=f32, device=dev)
         wgrad(dwp, g0T, tokT)
+        for s_ in side:
+            main.wait_stream(s_)
+        if sync is not None and prev is not None:
+            sync.launch(prev[0])
         grads["to_patch_embedding.weight"], grads["to_patch_embedding.bias"] = dwp, cs
         grads["cls_token"] = dcls.view(1, dim)
         grads["pos_emb.weight"] = dpos if dpos is not None else torch.zeros_like(model.pos_emb.weight)
@@ -302,6 +335,14 @@ class TsfTrainFunction(torch.autograd.Function):
             gr = grads.get(name)
             out.append(gr.view_as(p) if (gr is not None and p.requires_grad) else None)
         return tuple(out)
+
+
+def _side_streams(model, dev, count: int = 4):
+    st = getattr(model, "_side", None)
+    if st is None or st[0] != str(dev):
+        st = (str(dev), [torch.cuda.Stream(device=dev) for _ in range(count)])
+        model._side = st
+    return st[1]
 
 
 def _numel(shape) -> int:

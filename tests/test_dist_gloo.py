@@ -74,3 +74,41 @@ def test_shard_range_properties():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def _grad_sync_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import mintime_b200  # noqa: F401
+    from mintime_b200 import training
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sync = training.GradSync()
+    # three "layer buckets" launched one after the other as the backward would, finished together
+    buckets = [torch.full((1000 + 7 * i,), float(rank + 1) * (i + 1)) for i in range(3)]
+    views = [b[10:20] for b in buckets]                 # parameter gradients are views of the flat buckets
+    for b in buckets:
+        sync.launch(b)
+    sync.finish()
+    q.put((rank, [float(b[0]) for b in buckets], [float(v.sum()) for v in views], len(sync.pending)))
+    dist.destroy_process_group()
+
+
+def test_grad_sync_averages_layer_buckets_over_ranks():
+    """training.GradSync (the gradient exchange of train.py under data parallelism): per-layer flat buckets are
+    all-reduced asynchronously and averaged; views carved out of a bucket see the averaged values."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] == [1.5 * (i + 1) for i in range(3)]          # mean of (1, 2) * (i + 1)
+        assert r[2] == [15.0 * (i + 1) for i in range(3)]
+        assert r[3] == 0
