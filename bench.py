@@ -44,7 +44,8 @@ def load_peaks():
 class ClockSampler:
     """nvidia-smi polling during the timed region (B200_PROFILING.md 'clocks' recipe)."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_ms: int = 50):
+        self.period_ms = period_ms
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.index = index
@@ -56,7 +57,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"],
+                                          "-i", str(self.index), "-lms", str(self.period_ms)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

@@ -99,14 +99,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     for (int k = 0; k < 4; ++k) { dg[i][k] = 0.f; db[i][k] = 0.f; }
   }
   const float inv_dim = 1.0f / (float)dim;
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+  // software pipeline: the next row's x / dy loads are in flight while this row is reduced and written
+  const int stride = gridDim.x * 8;
+  int row = blockIdx.x * 8 + warp;
+  float nx[NV][4], nd[NV][4];
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      load4(x + (size_t)row * dim + (i * 32 + lane) * 4, nx[i]);
+      load4(dy + (size_t)row * dim + (i * 32 + lane) * 4, nd[i]);
+    }
+  }
+  for (; row < rows; row += stride) {
     float xv[NV][4], dv[NV][4];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      load4(x + (size_t)row * dim + (i * 32 + lane) * 4, xv[i]);
-      load4(dy + (size_t)row * dim + (i * 32 + lane) * 4, dv[i]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { xv[i][k] = nx[i][k]; dv[i][k] = nd[i][k]; }
       s += (xv[i][0] + xv[i][1]) + (xv[i][2] + xv[i][3]);
+    }
+    if (row + stride < rows) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        load4(x + (size_t)(row + stride) * dim + (i * 32 + lane) * 4, nx[i]);
+        load4(dy + (size_t)(row + stride) * dim + (i * 32 + lane) * 4, nd[i]);
+      }
     }
     const float mean = warp_sum(s) * inv_dim;
     float q = 0.f;
@@ -158,7 +176,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
-int ln_bwd_grid(int rows) { return std::min((rows + 7) / 8, sm_count() * 4); }
+int ln_bwd_grid(int rows) { return std::min((rows + 7) / 8, sm_count() * 2); }   // 2 resident blocks per SM (120 registers)
 
 template <typename T>
 int launch_ln_bwd(const float* x, const float* gamma, const void* dy, float* gx, float* part, int rows, int dim,

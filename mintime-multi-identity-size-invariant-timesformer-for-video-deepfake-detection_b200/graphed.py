@@ -83,3 +83,81 @@ class GraphedHotPath:
         s["positions"].copy_(positions, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class GraphedTrainStep:
+    """One training step of train.py:332-378 (frozen extractor forward, model forward, loss, ``loss.backward()``,
+    ``optimizer.step()``) captured as ONE CUDA graph for a fixed batch shape.
+
+    The eager step issues ~500 library launches plus ~400 small torch kernels from Python and is bound by that host
+    work; the replay is bound by the GPU.  Everything the step does is capturable: the library never allocates or
+    synchronises, the autograd node of ``training.py`` forks its weight-gradient GEMMs to side streams that join back
+    before it returns, the bf16 re-packing of the updated parameters is part of the captured forward, and SGD's foreach
+    update has no host dependency.  Fill ``static`` (videos, mask, identities_mask, size_embedding, positions, labels),
+    call ``replay()``; ``loss`` is the step's static output.  Single process only: the gradient exchange of a
+    data-parallel job (training.GradSync) is issued eagerly and is not captured.
+    """
+
+    def __init__(self, extractor, model, optimizer, loss_fn, batch: int, num_frames: int, frame_dtype=torch.uint8,
+                 device="cuda:0", num_patches: int = 49, warmup: int = 3):
+        self.device = torch.device(device)
+        _lib.require_device(self.device)
+        if getattr(model, "_grad_sync", None) is not None:
+            raise ValueError("GraphedTrainStep captures a single-process step; detach the gradient exchange first")
+        self.ext, self.model, self.opt, self.loss_fn = extractor, model, optimizer, loss_fn
+        self.b, self.f = batch, num_frames
+        d = self.device
+        self.static: Dict[str, torch.Tensor] = {
+            "videos": torch.zeros((batch, num_frames, 224, 224, 3), dtype=frame_dtype, device=d),
+            "mask": torch.ones((batch, num_frames), dtype=torch.bool, device=d),
+            "identities_mask": torch.ones((batch, num_frames, num_frames), dtype=torch.bool, device=d),
+            "size_embedding": torch.ones((batch, num_frames), dtype=torch.int32, device=d),
+            "positions": torch.arange(1 + num_frames * num_patches, dtype=torch.int64, device=d).repeat(batch, 1),
+            "labels": torch.zeros((batch, model.num_classes), dtype=torch.float32, device=d),
+        }
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss = None
+        self.logits = None
+        self.kernels_per_replay = 0
+        self._warmup = warmup
+
+    def _step(self):
+        s = self.static
+        with torch.no_grad():                                                              # train.py:344-346
+            x = s["videos"].view(self.b * self.f, 224, 224, 3).permute(0, 3, 1, 2)
+            feats = self.ext(x)
+            feats = feats.reshape(self.b, self.f, *feats.shape[1:])
+        self.model._train_pack = None          # the re-pack of the (just updated) parameters belongs to every step
+        y = self.model(feats, mask=s["mask"], size_embedding=s["size_embedding"], identities_mask=s["identities_mask"],
+                       positions=s["positions"])
+        if isinstance(y, tuple):
+            y = y[0]
+        loss = self.loss_fn(y, s["labels"])
+        loss.backward()
+        self.opt.step()
+        return loss.detach(), y.detach()
+
+    def capture(self):
+        """Run `warmup` eager steps on the CURRENT contents of ``static`` (they do update the parameters), then
+        capture the step."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self._warmup):
+                    self.opt.zero_grad(set_to_none=True)
+                    self._step()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            n0 = _lib.load().mt_prof_launch_count()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.logits = self._step()
+            self.kernels_per_replay = int(_lib.load().mt_prof_launch_count() - n0)
+        return self
+
+    def replay(self):
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        return self.loss

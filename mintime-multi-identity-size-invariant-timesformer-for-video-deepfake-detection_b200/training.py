@@ -219,19 +219,25 @@ class TsfTrainFunction(torch.autograd.Function):
         # nothing on the critical path reads them: they run on side streams, next to the main stream's kernels, and
         # their post-processing (q-row scale, GEGLU row order) follows them on the same side stream.
         main = torch.cuda.current_stream(dev)
-        side = _side_streams(model, dev)
+        # (model._serial_wgrad = True keeps them on the main stream: clean per-kernel timings for bench.py's table)
+        side = [main] if getattr(model, "_serial_wgrad", False) else _side_streams(model, dev)
         turn = [0]
 
-        def wgrad(dst, dyT, xT, after=None):
+        def wgrad(dst, dy, x, after=None, **dy_kw):
+            """dst += dy^T x on a side stream: both transposes (mt_grad_prep), the split-K GEMM and `after`."""
             s_ = side[turn[0] % len(side)]
             turn[0] += 1
-            s_.wait_stream(main)
+            if s_ is not main:
+                s_.wait_stream(main)
             with torch.cuda.stream(s_):
+                _, dyT, _ = ops.grad_prep(dy, want_t=True, precision=precision, **dy_kw)
+                _, xT, _ = ops.grad_prep(x, want_t=True, precision=precision)
                 ops.linear_wgrad_(dst, dyT, xT, precision)
                 if after is not None:
                     after()
-            for t in (dst, dyT, xT):
-                t.record_stream(s_)
+            if s_ is not main:
+                for t in (dst, dy, x):
+                    t.record_stream(s_)
 
         def side_done():
             evs = []
@@ -255,41 +261,37 @@ class TsfTrainFunction(torch.autograd.Function):
                     G[f"{j}.{k}"], off = _carve(flat, off, shape)
             # ---- feed-forward sub-block  x3 = x2 + W2 geglu(W1 LN(x2) + b1) + b2   (:65-76, :268)
             x_in, xn, h, go = S["ff"]
-            gb, gbT, cs = ops.grad_prep(g, want_rm=True, want_t=True, want_colsum=True, precision=precision)
+            # (gb: the T copy of g the GEMMs read; g itself keeps changing, so the side stream transposes gb)
+            gb, _, cs = ops.grad_prep(g, want_rm=True, want_colsum=True, precision=precision)
             G["2.fn.net.3.bias"].copy_(cs)
             dgo = ops.pointwise(gb, L["ff.w2_t"], precision=precision)
-            _, goT, _ = ops.grad_prep(go, want_t=True, precision=precision)
-            wgrad(G["2.fn.net.3.weight"], gbT, goT)
+            wgrad(G["2.fn.net.3.weight"], gb, go)
             dh_ = ops.geglu_bwd(h, dgo, precision)
-            del dgo, goT, gb, gbT
-            _, dhT, cs = ops.grad_prep(dh_, want_t=True, want_colsum=True, precision=precision)
-            _, xnT, _ = ops.grad_prep(xn, want_t=True, precision=precision)
+            del dgo, gb
+            _, _, cs = ops.grad_prep(dh_, want_colsum=True, precision=precision)
             dw1 = torch.zeros((8 * dim, dim), dtype=f32, device=dev)      # interleaved row order of the packed weight
-            wgrad(dw1, dhT, xnT, after=lambda dw1=dw1, dst=G["2.fn.net.0.weight"]: dst.copy_(_uninterleave(dw1)))
+            wgrad(dw1, dh_, xn, after=lambda dw1=dw1, dst=G["2.fn.net.0.weight"]: dst.copy_(_uninterleave(dw1)))
             G["2.fn.net.0.bias"].copy_(_uninterleave(cs))
             dxn = ops.pointwise(dh_, L["ff.w1_t"], precision=precision)
-            del dh_, dhT, xnT, dw1
+            del dh_, dw1
             dgm, dbt = ops.layernorm_bwd_(g, x_in, L["ff.ln_g"], dxn, precision)
             G["2.norm.weight"].copy_(dgm)
             G["2.norm.bias"].copy_(dbt)
             # ---- attention sub-blocks, space then time   x' = x + Wo attn(Wqkv LN(x)) + bo   (:109-144, :265-267)
             for j, name in ((1, "space"), (0, "time")):
                 x_in, xn, qkv, ao = S[name]
-                gb, gbT, cs = ops.grad_prep(g, want_rm=True, want_t=True, want_colsum=True, precision=precision)
+                gb, _, cs = ops.grad_prep(g, want_rm=True, want_colsum=True, precision=precision)
                 G[f"{j}.fn.to_out.0.bias"].copy_(cs)
                 dao = ops.pointwise(gb, L[name + ".wo_t"], precision=precision)
-                _, aoT, _ = ops.grad_prep(ao, want_t=True, precision=precision)
-                wgrad(G[f"{j}.fn.to_out.0.weight"], gbT, aoT)
+                wgrad(G[f"{j}.fn.to_out.0.weight"], gb, ao)
                 dqkv = ops.divided_attention_bwd(qkv.view(B, N, -1), dao.view(B, N, -1), mask_u8, idm_u8, name, f, n,
                                                  heads, dh, precision).view(M, -1)
-                del dao, aoT, gb, gbT
-                _, dqkvT, _ = ops.grad_prep(dqkv, want_t=True, precision=precision)
-                _, xnT, _ = ops.grad_prep(xn, want_t=True, precision=precision)
+                del dao, gb
                 wq = G[f"{j}.fn.to_qkv.weight"]
                 # (the packed q rows carry dim_head^-0.5, :114)
-                wgrad(wq, dqkvT, xnT, after=lambda wq=wq: wq[:inner].mul_(scale))
+                wgrad(wq, dqkv, xn, after=lambda wq=wq: wq[:inner].mul_(scale))
                 dxn = ops.pointwise(dqkv, L[name + ".wqkv_t"], precision=precision)
-                del dqkv, dqkvT, xnT
+                del dqkv
                 dgm, dbt = ops.layernorm_bwd_(g, x_in, L[name + ".ln_g"], dxn, precision)
                 G[f"{j}.norm.weight"].copy_(dgm)
                 G[f"{j}.norm.bias"].copy_(dbt)
@@ -309,12 +311,12 @@ class TsfTrainFunction(torch.autograd.Function):
         dpos, dsize, dcls = ops.embed_bwd(g3, pos, se, rows, f, n, want_pos=bool(model.enable_pos_emb),
                                           want_size=bool(model.enable_size_emb))
         Mt = B * f * n
-        _, g0T, cs = ops.grad_prep(g, want_t=True, want_colsum=True, rows_per_batch=f * n, m=Mt, precision=precision)
-        _, tokT, _ = ops.grad_prep(tok.view(Mt, -1), want_t=True, precision=precision)
+        _, _, cs = ops.grad_prep(g, want_colsum=True, rows_per_batch=f * n, m=Mt, precision=precision)
         dwp = torch.zeros((dim, model.channels), dtype=f32, device=dev)
-        wgrad(dwp, g0T, tokT)
+        wgrad(dwp, g, tok.view(Mt, -1), rows_per_batch=f * n, m=Mt)     # (g is final here: nothing writes it any more)
         for s_ in side:
-            main.wait_stream(s_)
+            if s_ is not main:
+                main.wait_stream(s_)
         if sync is not None and prev is not None:
             sync.launch(prev[0])
         grads["to_patch_embedding.weight"], grads["to_patch_embedding.bias"] = dwp, cs

@@ -304,3 +304,51 @@ def test_eval_after_train_uses_updated_weights_and_frozen_params_get_no_grad():
         model(x.clone().float().requires_grad_(True).bfloat16(), mask=meta["mask"].to(DEV),
               size_embedding=meta["size_embedding"], identities_mask=meta["identities_mask"].to(DEV),
               positions=meta["positions"].to(DEV))
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """GraphedTrainStep (one CUDA-graph replay per train.py step) follows the eager loop: same losses and parameters
+    after the same number of SGD steps on the same batch (fp32 atomics in the embedding tables: allclose, not equal)."""
+    from mintime_b200 import EfficientNet, synth
+    from mintime_b200.graphed import GraphedTrainStep
+    case = "b3_f16_mixed_d2"
+    cfg, tsd, meta, _, labels, pw = grad_case_inputs(case)
+    B, f = 3, 16
+    ext = EfficientNet.from_name("efficientnet-b0", precision="bf16")
+    ext.load_state_dict(synth.make_effnet_state_dict(1234))
+    ext = ext.to(DEV).eval()
+    frames = synth.make_frames(B, f, seed=7, mask=meta["mask"], dtype=torch.uint8).to(DEV)
+    lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw], device=DEV))
+
+    def make():
+        m = SizeInvariantTimeSformer(config=cfg, precision="bf16")
+        m.load_state_dict(tsd)
+        m = m.to(DEV).train()
+        return m, torch.optim.SGD(m.parameters(), lr=0.01, weight_decay=1e-4)
+
+    # eager: 3 warm-up steps + 3 more
+    model, opt = make()
+    eager = []
+    for _ in range(6):
+        with torch.no_grad():
+            feats = ext(frames.view(B * f, 224, 224, 3).permute(0, 3, 1, 2)).reshape(B, f, 1280, 7, 7)
+        opt.zero_grad(set_to_none=True)
+        y = model(feats, mask=meta["mask"].to(DEV), size_embedding=meta["size_embedding"],
+                  identities_mask=meta["identities_mask"].to(DEV), positions=meta["positions"].to(DEV))
+        loss = lossf(y, labels.to(DEV))
+        loss.backward()
+        opt.step()
+        eager.append(loss.item())
+    # graphed: 3 eager warm-up steps inside capture(), the capture itself does not execute, then 3 replays
+    model2, opt2 = make()
+    gs = GraphedTrainStep(ext, model2, opt2, lossf, B, f, frame_dtype=torch.uint8, device=DEV, warmup=3)
+    gs.static["videos"].copy_(frames)
+    for k in ("mask", "identities_mask", "size_embedding", "positions"):
+        gs.static[k].copy_(meta[k])
+    gs.static["labels"].copy_(labels)
+    gs.capture()
+    assert gs.kernels_per_replay > 150                       # extractor + 2-layer forward and backward, all in the graph
+    got = [gs.replay().item() for _ in range(3)]
+    assert np.allclose(got, eager[3:], rtol=0, atol=2e-3), (got, eager)
+    for (k, p), q in zip(model.named_parameters(), model2.parameters()):
+        assert rel_err(q, p) <= 2e-3, k
