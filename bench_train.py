@@ -43,6 +43,62 @@ def cpu_train_videos_per_sec(batch, frames, identities, steps=2):
     return batch / sec, sec, torch.get_num_threads()
 
 
+class NvmlSampler:
+    """Clocks / throttle reasons DURING the timed region from an in-process NVML thread.  (bench.py's nvidia-smi poller
+    re-initialises NVML on every sample; its driver locks stall the ~900 host-side launches of an eager training step:
+    25.7 -> 34 ms at a 50 ms period, 39 ms on the polled GPU of a 2-GPU run.)"""
+
+    def __init__(self, index: int, period_s: float = 0.05):
+        import threading
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.window = "warm-up + timed region"
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self.ok = False
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self._thread.start()
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(get(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        s = sorted(self.samples)
+        load = s[len(s) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s), "window": self.window, "source": "in-process NVML thread, 50 ms period"}
+
+
 def run_train(args, emit, ClockSampler, load_peaks):
     import mintime_b200
     from mintime_b200 import _lib, synth, training
@@ -148,11 +204,11 @@ def run_train(args, emit, ClockSampler, load_peaks):
         return mdist.max_over_ranks(ms, device=dev)
 
     lib = _lib.load()
-    # (a 50 ms nvidia-smi poll slows this host-launch-heavy step by a third: NVML queries serialise with launches)
-    sampler = ClockSampler(local_rank, period_ms=250)
+    sampler = NvmlSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
+    # (the first steps of a data-parallel run still set up NCCL channels and grow the side-stream allocator pools)
+    for _ in range(max(args.warmup, 8)):
         step_resident()
     torch.cuda.synchronize()
     launches0 = lib.mt_prof_launch_count()
@@ -161,12 +217,6 @@ def run_train(args, emit, ClockSampler, load_peaks):
     launches = lib.mt_prof_launch_count() - launches0
     if use_graph:
         launches = graph_kernels * args.steps
-    if rank == 0 and world == 1 and time.perf_counter() - t_wall < 1.0:
-        # keep the SAME step running (untimed) until the slow poller has seen about a second of this load
-        sampler.window = "warm-up + timed region + untimed continuation of the same step (250 ms poller)"
-        while time.perf_counter() - t_wall < 1.0:
-            step_resident()
-            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     lib.mt_prof_reset()
@@ -210,7 +260,7 @@ def run_train(args, emit, ClockSampler, load_peaks):
     h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
     emit({
         "metric": "train_videos_per_sec_16f_224px", "value": world * B / (ms * 1e-3), "unit": "videos/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": max(args.warmup, 8), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": "BASELINE.json configs[3]: train.py step, frozen EfficientNet-B0 (eval, no_grad) -> "
                                "SizeInvariantTimeSformer forward + backward + SGD, synthetic ForgeryNet-shaped clips",
