@@ -151,7 +151,11 @@ class GraphedTrainStep:
             self.graph = torch.cuda.CUDAGraph()
             self.opt.zero_grad(set_to_none=True)
             n0 = _lib.load().mt_prof_launch_count()
-            with torch.cuda.graph(self.graph):
+            # MINTIME_B200_TRAIN_PRIO=1: capture on a high-priority stream, so the kernel nodes of the critical path
+            # outrank the weight-gradient work forked to the (default-priority) side streams
+            import os
+            cap = torch.cuda.Stream(priority=-1) if os.environ.get("MINTIME_B200_TRAIN_PRIO", "0") == "1" else None
+            with torch.cuda.graph(self.graph, stream=cap):
                 self.loss, self.logits = self._step()
             self.kernels_per_replay = int(_lib.load().mt_prof_launch_count() - n0)
         return self

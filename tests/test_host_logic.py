@@ -109,6 +109,17 @@ def test_no_cpu_fallback():
         t(torch.zeros(1, 16, 1280, 7, 7), mask=torch.ones(1, 16, dtype=torch.bool),
           identities_mask=torch.ones(1, 16, 16, dtype=torch.bool),
           size_embedding=torch.zeros(1, 16, dtype=torch.int32), positions=torch.zeros(1, 785, dtype=torch.int64))
+    t.train()                                          # the training step (autograd node) has no CPU route either
+    assert torch.is_grad_enabled() and all(p.requires_grad for p in t.parameters())
+    with pytest.raises(_lib.MintimeError):
+        t(torch.zeros(1, 16, 1280, 7, 7), mask=torch.ones(1, 16, dtype=torch.bool),
+          identities_mask=torch.ones(1, 16, 16, dtype=torch.bool),
+          size_embedding=torch.zeros(1, 16, dtype=torch.int32), positions=torch.zeros(1, 785, dtype=torch.int64))
+    from mintime_b200 import ops
+    with pytest.raises(_lib.MintimeError):
+        ops.layernorm_bwd_(torch.zeros(8, 512), torch.zeros(8, 512), torch.ones(512), torch.zeros(8, 512).bfloat16())
+    with pytest.raises(_lib.MintimeError):
+        ops.grad_prep(torch.zeros(64, 64), want_t=True)
     e = EfficientNet.from_name("efficientnet-b0")      # train mode is not implemented: loud, not silent
     with pytest.raises(NotImplementedError):
         e(torch.zeros(1, 3, 224, 224))
