@@ -253,9 +253,15 @@ def run_train(args, emit, ClockSampler, load_peaks):
                         "frac": ach / peak})
     dom = kernels[0] if kernels else None
     roofline = None
+    traffic = {}
+    try:     # per-launch dram bytes (ncu --set full, profiles/r1_train_kernels_ncu_summary.txt)
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic_train.json")) as fh:
+            traffic = json.load(fh)
+    except Exception:
+        pass
     if dom:
         roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
-                    "frac": dom["frac"], "traffic": None, "kernel": dom["name"], "share_of_step": dom["share"],
+                    "frac": dom["frac"], "traffic": traffic.get(dom["name"]), "kernel": dom["name"], "share_of_step": dom["share"],
                     "ms_per_launch": dom["ms_per_launch"], "peak_source": peaks["source"]}
     h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
     emit({

@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <mutex>
 
+#include <stdio.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -937,8 +939,11 @@ int launch_gemm(int precision, const GemmArgs& g, cudaStream_t stream) {
   else if (g.epi.kind == EPI_RESID_F32) bytes += mn * 8;
   else if (g.epi.kind == EPI_GEGLU) bytes += mn / 2 * es;
   else if (g.epi.kind == EPI_PATCH_EMBED) bytes += mn * 4 * (g.epi.size_tab ? 3 : 2);
-  ProfScope prof(stream, 2.0 * mn * g.K, bytes, "gemm_%s %s%s N%d K%d", precision == MT_PREC_BF16 ? "tc" : "simt",
-                 (g.epi.kind >= 0 && g.epi.kind < 4) ? kKind[g.epi.kind] : "?", gated ? "+gate" : "", g.N, g.K);
+  // (split-K weight gradients carry M in the name: three shapes share N = 512, K = tokens)
+  char wg[24] = "";
+  if (g.splits > 1) snprintf(wg, sizeof(wg), " wgrad M%d", g.M);
+  ProfScope prof(stream, 2.0 * mn * g.K, bytes, "gemm_%s %s%s%s N%d K%d", precision == MT_PREC_BF16 ? "tc" : "simt",
+                 (g.epi.kind >= 0 && g.epi.kind < 4) ? kKind[g.epi.kind] : "?", gated ? "+gate" : "", wg, g.N, g.K);
   switch (g.epi.kind) {
     case EPI_STORE:
       return gated ? dispatch_prec<EPI_STORE, true>(precision, g, stream)

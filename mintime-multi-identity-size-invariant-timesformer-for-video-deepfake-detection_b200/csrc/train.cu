@@ -572,7 +572,8 @@ int launch_attn_bwd(const void* qkv_, const void* dout_, const uint8_t* mask, co
   float* ws_q = reinterpret_cast<float*>(ws + l.q);
   float* ws_cls = reinterpret_cast<float*>(ws + l.cls);
   {
-    ProfScope prof(st, 10.0 * B * heads * 64.0 * N, (double)B * N * heads * 64 * (2 * sizeof(T) + 512.0), "attn_cls_bwd");
+    // K, V of every token read once, the fp32 dK / dV contributions of the CLS row written once
+    ProfScope prof(st, 10.0 * B * heads * 64.0 * N, (double)B * N * heads * (64.0 * 2 * sizeof(T) + 512.0), "attn_cls_bwd");
     const size_t smem = (size_t)(2 * N + 64 + 64 + 32 + 2048) * sizeof(float);
     auto kern = attn_cls_bwd_kernel<T>;
     if (smem > 48 * 1024) {
@@ -584,7 +585,7 @@ int launch_attn_bwd(const void* qkv_, const void* dout_, const uint8_t* mask, co
   }
   const int G = mode == MT_ATTN_TIME ? n : f, Gq = mode == MT_ATTN_TIME ? f : n, Gk = Gq + 1;
   {
-    ProfScope prof(st, 10.0 * B * heads * G * 64.0 * Gq * Gk, (double)B * N * heads * 64 * (7.0 * sizeof(T) + 512.0),
+    ProfScope prof(st, 10.0 * B * heads * G * 64.0 * Gq * Gk, (double)B * N * heads * (64.0 * 7 * sizeof(T) + 512.0),   // q, k, v, dO in; dq, dk, dv out; workspace row in
                    mode == MT_ATTN_TIME ? "attn_time_bwd" : "attn_space_bwd");
     const size_t smem = (size_t)(2 * Gk * 65 + 2 * Gq * 65 + 2 * Gq * 64) * sizeof(float);
     int rc_mma = MT_ERR_UNSUPPORTED;
@@ -776,7 +777,8 @@ extern "C" int mt_grad_prep(int precision, const void* src, int src_is_f32, void
   }
   dim3 grid(c / 64, tiles_m);
   {
-    ProfScope prof(st, 0.0, (double)m * c * ((src_is_f32 ? 4 : es) + (out_rm ? es : 0) + (out_t ? es : 0)), "grad_prep");
+    ProfScope prof(st, 0.0, (double)m * c * ((src_is_f32 ? 4 : es) + (out_rm ? es : 0) + (out_t ? es : 0)), "grad_prep C%d%s%s%s", c,
+                   src_is_f32 ? " f32" : "", out_rm ? " cast" : "", out_t ? " T" : "");
     const bool f32 = precision == MT_PREC_FP32;
     if (src_is_f32 || f32) {
       if (f32)
