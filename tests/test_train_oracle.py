@@ -51,3 +51,35 @@ def test_layer_gradient_layout_covers_every_layer_parameter():
                                                   (2, training._ff_layout(dim))) for k, s in lay}
     got = {k: tuple(p.shape) for k, p in model.named_parameters() if k.startswith("layers.0.")}
     assert names == got
+
+
+def test_train_pack_layouts_on_cpu():
+    """TrainPack (device-side re-packing of the live parameters, redone after every optimizer step): transposed copies
+    for the dgrad GEMMs, q rows pre-scaled by dim_head^-0.5 (:114), GEGLU rows interleaved like the inference pack."""
+    from mintime_b200 import SizeInvariantTimeSformer, synth
+    from mintime_b200.spec import default_tsf_config
+    cfg = default_tsf_config(num_frames=8)
+    cfg["model"]["depth"] = 2
+    model = SizeInvariantTimeSformer(config=cfg, precision="fp32")
+    sd = synth.make_tsf_state_dict(cfg, 5)
+    model.load_state_dict(sd)
+    pk = training.TrainPack(model, "fp32", "cpu")
+    ref = weights.pack_tsf(sd, cfg, "fp32", "cpu")
+    assert len(pk.layers) == 2
+    for l, L in enumerate(pk.layers):
+        for j, name in ((0, "time"), (1, "space")):
+            wq = sd[f"layers.{l}.{j}.fn.to_qkv.weight"].clone()
+            wq[:512] *= 0.125
+            assert torch.equal(L[name + ".wqkv"], wq) and torch.equal(L[name + ".wqkv_t"], wq.t().contiguous())
+            assert L[name + ".wqkv_t"].is_contiguous() and L[name + ".wqkv_t"].shape == (512, 1536)
+            assert torch.equal(L[name + ".wo_t"], sd[f"layers.{l}.{j}.fn.to_out.0.weight"].t())
+        w1 = weights.geglu_interleave(sd[f"layers.{l}.2.fn.net.0.weight"])
+        assert torch.equal(L["ff.w1"], w1) and torch.equal(L["ff.w1_t"], w1.t().contiguous())
+        assert torch.equal(L["ff.b1"], weights.geglu_interleave(sd[f"layers.{l}.2.fn.net.0.bias"]))
+        assert torch.equal(L["ff.w2_t"], sd[f"layers.{l}.2.fn.net.3.weight"].t())
+    # the same bytes as the load-time pack of the inference path (so both paths read identical weights)
+    packed_ref = {t.data_ptr(): t for t in ref.keep}
+    assert torch.equal(pk.layers[0]["ff.w1"], packed_ref[ref.struct.ff[0].w1])
+    assert torch.equal(pk.layers[1]["time.wqkv"], packed_ref[ref.struct.time_attn[1].w_qkv])
+    # fp32 parameters are read in place (no copy): an optimizer step is visible without re-packing them
+    assert pk.out_w.data_ptr() == model.to_out[1].weight.data_ptr()
