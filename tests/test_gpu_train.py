@@ -352,3 +352,26 @@ def test_graphed_train_step_matches_eager_steps():
     assert np.allclose(got, eager[3:], rtol=0, atol=2e-3), (got, eager)
     for (k, p), q in zip(model.named_parameters(), model2.parameters()):
         assert rel_err(q, p) <= 2e-3, k
+
+
+def test_training_forward_returns_attention_maps_too():
+    """require_attention=True in a training step (the reference returns (logits, [space, time]) in any mode, :271-276):
+    the maps equal the inference path's, carry no gradient, and loss.backward() still fills every parameter."""
+    case = "b3_f16_mixed_d2"
+    cfg, tsd, meta, feats, labels, pw = grad_case_inputs(case)
+    model = SizeInvariantTimeSformer(config=cfg, require_attention=True, precision="bf16")
+    model.load_state_dict(tsd)
+    model = model.to(DEV).train()
+    x = feats.to(DEV).bfloat16()
+    kw = dict(mask=meta["mask"].to(DEV), size_embedding=meta["size_embedding"],
+              identities_mask=meta["identities_mask"].to(DEV), positions=meta["positions"].to(DEV))
+    y, (sa, ta) = model(x, **kw)
+    assert y.requires_grad and not sa.requires_grad and not ta.requires_grad
+    assert sa.shape == (3 * 8, 1, 785) and ta.shape == (3 * 8, 1, 785)
+    torch.nn.functional.binary_cross_entropy_with_logits(y, labels.to(DEV)).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    with torch.no_grad():
+        y2, (sa2, ta2) = model(x, **kw)
+    assert (y2 - y.detach()).abs().max() <= 2e-2
+    assert rel_err(sa, sa2) <= 1e-2 and rel_err(ta, ta2) <= 1e-2
+    assert torch.allclose(sa.sum(-1), torch.ones_like(sa.sum(-1)), atol=1e-3)
