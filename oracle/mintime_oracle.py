@@ -116,6 +116,68 @@ def effnet_b0_forward(sd: Dict[str, Tensor], x: Tensor, taps: Optional[dict] = N
 
 
 # ----------------------------------------------------------------------------------------------
+# EfficientNet-B0 in TRAIN mode (train.py:155-170 unfrozen extractor).  Not yet built in the
+# product (the shim raises); this is the pinned checker the backward kernels of the extractor will be
+# held to: BatchNorm with batch statistics + running-stat update, drop-connect, autograd for gradients.
+# ----------------------------------------------------------------------------------------------
+BN_MOMENTUM = 0.01           # 1 - batch_norm_momentum (0.99), model.py:47 / utils.py:520
+DROP_CONNECT_RATE = 0.2      # utils.py:523
+
+
+def bn_train(x: Tensor, sd: Dict[str, Tensor], p: str, new_stats: Optional[dict]) -> Tensor:
+    """nn.BatchNorm2d in train mode: normalise with the batch's biased variance; running stats move by
+    momentum 0.01 towards the batch mean / UNBIASED variance (returned in ``new_stats``, ``sd`` untouched)."""
+    if new_stats is not None:
+        with torch.no_grad():
+            n = x.numel() // x.shape[1]
+            mean = x.mean(dim=(0, 2, 3))
+            var_u = x.var(dim=(0, 2, 3), unbiased=True) if n > 1 else torch.zeros_like(mean)
+            new_stats[p + '.running_mean'] = (1 - BN_MOMENTUM) * sd[p + '.running_mean'] + BN_MOMENTUM * mean
+            new_stats[p + '.running_var'] = (1 - BN_MOMENTUM) * sd[p + '.running_var'] + BN_MOMENTUM * var_u
+    return F.batch_norm(x, None, None, sd[p + '.weight'], sd[p + '.bias'], True, 0.0, BN_EPS)
+
+
+def drop_connect(x: Tensor, p: float) -> Tensor:
+    """utils.py:129-154 (training): per-sample keep mask floor(keep_prob + U[0,1)), survivors scaled by 1/keep_prob.
+    Draws from torch's global RNG exactly like the reference (same call, same shape, same order)."""
+    keep = 1 - p
+    r = keep + torch.rand([x.shape[0], 1, 1, 1], dtype=x.dtype, device=x.device)
+    return x / keep * torch.floor(r)
+
+
+def mbconv_train(x: Tensor, sd, p: str, b: dict, drop_rate: float, new_stats: Optional[dict]) -> Tensor:
+    """MBConvBlock.forward in train mode, model.py:89-128."""
+    inp = x
+    if b['e'] != 1:
+        x = swish(bn_train(F.conv2d(x, sd[p + '_expand_conv.weight']), sd, p + '_bn0', new_stats))
+    cexp = x.shape[1]
+    x = F.conv2d(same_pad(x, b['k'], b['s']), sd[p + '_depthwise_conv.weight'], None, b['s'], 0, 1, cexp)
+    x = swish(bn_train(x, sd, p + '_bn1', new_stats))
+    sq = F.adaptive_avg_pool2d(x, 1)
+    sq = swish(F.conv2d(sq, sd[p + '_se_reduce.weight'], sd[p + '_se_reduce.bias']))
+    sq = F.conv2d(sq, sd[p + '_se_expand.weight'], sd[p + '_se_expand.bias'])
+    x = torch.sigmoid(sq) * x
+    x = bn_train(F.conv2d(x, sd[p + '_project_conv.weight']), sd, p + '_bn2', new_stats)
+    if b['skip']:
+        if drop_rate:                                                       # model.py:125-126
+            x = drop_connect(x, drop_rate)
+        x = x + inp
+    return x
+
+
+def effnet_b0_forward_train(sd: Dict[str, Tensor], x: Tensor, drop_connect_rate: float = DROP_CONNECT_RATE,
+                            new_stats: Optional[dict] = None) -> Tensor:
+    """EfficientNet.forward with ``.train()`` (model.py:267-288): per-block drop-connect rate
+    ``drop_connect_rate * idx / 16`` (model.py:279-282).  ``new_stats`` receives the updated BatchNorm running stats."""
+    x = swish(bn_train(F.conv2d(same_pad(x, 3, 2), sd['_conv_stem.weight'], None, 2), sd, '_bn0', new_stats))
+    blocks = decode_blocks()
+    for i, b in enumerate(blocks):
+        rate = drop_connect_rate * float(i) / len(blocks) if drop_connect_rate else 0.0
+        x = mbconv_train(x, sd, f'_blocks.{i}.', b, rate, new_stats)
+    return swish(bn_train(F.conv2d(x, sd['_conv_head.weight']), sd, '_bn1', new_stats))
+
+
+# ----------------------------------------------------------------------------------------------
 # Size-Invariant TimeSformer
 # ----------------------------------------------------------------------------------------------
 def _ln(x: Tensor, sd, p: str) -> Tensor:

@@ -81,3 +81,21 @@ def grad_case_inputs(name):
     feats = feats.bfloat16().float()
     labels = torch.tensor([[float(i % 2 == 0)] for i in range(B)])
     return cfg, tsd, meta, feats, labels, 0.8169
+
+
+# ---------------------------------------------------------------------------------------------------
+# extractor in train mode (oracle/make_golden_extractor_train.py)
+# ---------------------------------------------------------------------------------------------------
+EXTRACTOR_TRAIN_KEYS = ["_conv_stem.weight", "_bn0.weight", "_blocks.0._depthwise_conv.weight", "_blocks.1._expand_conv.weight",
+                        "_blocks.2._se_reduce.weight", "_blocks.5._bn1.bias", "_blocks.10._project_conv.weight",
+                        "_blocks.15._se_expand.bias", "_conv_head.weight", "_bn1.weight"]
+
+
+def extractor_train_inputs():
+    """(effnet state_dict, 4 faces (4,3,224,224) raw 0..255, probe (4,1280,7,7)) for the train-mode extractor fixture"""
+    esd = synth.make_effnet_state_dict(1234)
+    meta = synth.make_batch_meta(1, 4, [1], seed=11, pad_tail=False)
+    frames = synth.make_frames(1, 4, seed=11, mask=meta["mask"])                 # (1,4,224,224,3)
+    x = frames.view(4, 224, 224, 3).permute(0, 3, 1, 2).contiguous()
+    probe = torch.randn((4, 1280, 7, 7), generator=torch.Generator().manual_seed(3))
+    return esd, x, probe

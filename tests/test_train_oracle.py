@@ -83,3 +83,27 @@ def test_train_pack_layouts_on_cpu():
     assert torch.equal(pk.layers[1]["time.wqkv"], packed_ref[ref.struct.time_attn[1].w_qkv])
     # fp32 parameters are read in place (no copy): an optimizer step is visible without re-packing them
     assert pk.out_w.data_ptr() == model.to_out[1].weight.data_ptr()
+
+
+@pytest.mark.parametrize("tag,rate", [("nodrop", 0.0), ("drop", 0.2)])
+def test_oracle_extractor_train_mode_matches_reference(tag, rate):
+    """oracle.effnet_b0_forward_train (BatchNorm batch statistics + running-stat update, drop-connect with the reference's
+    RNG draws, autograd gradients) against the unmodified reference in .train() -- the checker for the extractor's
+    backward kernels (not built in the product yet, which raises instead)."""
+    from helpers import EXTRACTOR_TRAIN_KEYS, extractor_train_inputs
+    gold = load_golden("extractor_train")
+    esd, x, probe = extractor_train_inputs()
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in esd.items()}
+    new_stats = {}
+    torch.manual_seed(7)
+    out = orc.effnet_b0_forward_train(sd, x, drop_connect_rate=rate, new_stats=new_stats)
+    (out * probe).sum().backward()
+    scale = float(gold[f"{tag}.out_absmean"])
+    assert np.abs(sample(out) - gold[f"{tag}.out"]).max() <= 2e-4 * max(scale, 1.0)
+    for k in EXTRACTOR_TRAIN_KEYS:
+        ref = gold[f"{tag}.grad.{k}"]
+        got = sample(sd[k].grad, 512)
+        assert np.linalg.norm(got - ref) <= 2e-3 * np.linalg.norm(ref) + 1e-8, k
+    for k in ("_bn0", "_blocks.0._bn1", "_blocks.5._bn0", "_blocks.15._bn2", "_bn1"):
+        assert np.allclose(new_stats[k + ".running_mean"].numpy(), gold[f"{tag}.{k}.running_mean"], rtol=1e-4, atol=1e-5), k
+        assert np.allclose(new_stats[k + ".running_var"].numpy(), gold[f"{tag}.{k}.running_var"], rtol=1e-4, atol=1e-5), k
