@@ -169,6 +169,8 @@ _device_ok = set()
 def require_device(device) -> None:
     """Raise unless `device` is a CUDA device the library supports (compute capability 10.x)."""
     import torch
+    if isinstance(device, torch.device) and device.type == "cuda" and device.index in _device_ok:
+        return                      # hot path of the eager training step: ~500 calls per step
     if not torch.cuda.is_available():
         raise MintimeError("mintime_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     dev = torch.device(device)
