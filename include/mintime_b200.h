@@ -24,8 +24,9 @@
 extern "C" {
 #endif
 
-#define MT_ABI_VERSION 3   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
-                            * 3: + the backward entry points of the transformer (mt_*_bwd, mt_grad_prep, mt_geglu_*) */
+#define MT_ABI_VERSION 4   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
+                            * 3: + the backward entry points of the transformer (mt_*_bwd, mt_grad_prep, mt_geglu_*)
+                            * 4: mt_clip_meta_fwd mask_padding semantics; fused divided attention; extractor training */
 
 enum { MT_PREC_FP32 = 0, MT_PREC_BF16 = 1 };
 enum { MT_OK = 0, MT_ERR_ARG = -1, MT_ERR_WORKSPACE = -2, MT_ERR_UNSUPPORTED = -3, MT_ERR_DRIVER = -4 };
@@ -187,11 +188,14 @@ int mt_expand_dwconv_fwd(const void* in, const void* w_exp, const float* exp_shi
  * predict.py generate_masks (:254-352), from the per-identity slot table of each clip:
  *   slots, n_real i32 [batch][max_identities]: face slots owned by each identity (sum <= f) and how many hold a face;
  *   frame_no, ratio i32 [batch][f]: source frame number and int(face_area*100/video_area) of the face in each slot
- *   identity_attention: 0 -> every slot is valid (deepfakes_dataset.py:285-286)
+ *   mask_padding: 1 -> padded slots get mask 0 (predict.py:300-306); 0 -> every slot is valid, which is what
+ *   DeepFakesDataset.__getitem__ returns AS EXECUTED (its test at :283 runs after :276 has padded the list, so the
+ *   all-ones branch :286 is always taken; tests/golden/clip_meta_ref.json holds outputs of the reference class).
+ *   Padded slots repeat the largest frame number of the clip so far (:277, predict.py:304).
  * -> mask u8 [batch][f], identities_mask u8 [batch][f][f], size_embedding i32 [batch][f] (0 = padding, 1..20 = size
  *    bucket), positions i64 [batch][1 + f*n_patches] -- the tensors mt_tsf_fwd / the forward of the model take. */
 int mt_clip_meta_fwd(const int32_t* slots, const int32_t* n_real, const int32_t* frame_no, const int32_t* ratio,
-                     int max_identities, int identity_attention, uint8_t* mask, uint8_t* identities_mask,
+                     int max_identities, int mask_padding, uint8_t* mask, uint8_t* identities_mask,
                      int32_t* size_embedding, int64_t* positions, int batch, int f, int n_patches, void* stream);
 
 /* Stem: ZeroPad2d(0,1,0,1) + conv 3x3 s2 (3->32) + BN + swish (utils.py:248-276, model.py:276)

@@ -147,7 +147,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         if name.endswith(("_fwd", "_bwd")) or name in ("mt_grad_prep", "mt_colsum_f32", "mt_linear_wgrad"):
             fn.restype = i32
-    if lib.mt_abi_version() != 3:
+    if lib.mt_abi_version() != 4:
         raise RuntimeError("mintime_b200: ABI version mismatch between _lib.py and libmintime_b200.so")
     _lib = lib
     return lib

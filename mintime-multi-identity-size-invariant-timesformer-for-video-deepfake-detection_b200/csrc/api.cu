@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -24,6 +25,28 @@ void set_error(const char* fmt, ...) {
 int cuda_status(cudaError_t e, const char* what) {
   set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
   return (int)e;
+}
+
+namespace {
+std::mutex g_once_mu;
+std::vector<std::pair<int, const void*>> g_once;
+}  // namespace
+
+bool first_use_on_device(const void* key) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_once_mu);
+  for (const auto& e : g_once)
+    if (e.first == dev && e.second == key) return false;
+  g_once.emplace_back(dev, key);
+  return true;
+}
+
+int current_sms() {
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
 }
 
 // ---------------------------------------------------------------------------------- diagnostics

@@ -273,11 +273,9 @@ int launch_group_bwd_mma(const bf16* qkv, const bf16* dout, const uint8_t* mask,
   const int G = MODE == MT_ATTN_TIME ? n : f;
   const int total = B * heads * G;
   auto kern = attn_group_bwd_mma_kernel<MODE, MT, NKT, GPB>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(kern))) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GPB * kSlot);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(attn_group_bwd_mma)");
-    attr_set = true;
   }
   kern<<<(total + GPB - 1) / GPB, 128, GPB * kSlot, st>>>(qkv, dout, mask, idmask, dqkv, ws_kv, ws_cls, f, n, heads, total);
   cudaError_t e = cudaGetLastError();

@@ -24,6 +24,11 @@ int cuda_status(cudaError_t e, const char* what);
     }                             \
   } while (0)
 
+// Function attributes (dynamic shared-memory opt-in, carve-out) are PER DEVICE: true the first time `key` (a kernel's
+// address) is seen on the calling thread's current device, so a process that touches a second GPU opts in there too.
+bool first_use_on_device(const void* key);
+int current_sms();     // multiprocessor count of the current device
+
 // ------------------------------------------------------------------ diagnostics (mt_prof_* in the C ABI)
 void count_launch();
 // When profiling is enabled, brackets the launches issued in its scope with CUDA events on `stream`

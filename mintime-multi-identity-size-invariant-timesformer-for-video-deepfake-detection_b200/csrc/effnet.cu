@@ -8,9 +8,8 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "attention_mma.cuh"   // mma.sync / pack2 wrappers (stem_tc_kernel)
 #include "dwconv_simt.cuh"
-#include "dwconv_tc.cuh"
-#include "dwconv_umma.cuh"
 #include "mbconv_fused.cuh"
 
 namespace mt {
@@ -276,7 +275,10 @@ inline DwGeom dw_geom(int H, int W, int C, int k, int s) {
 // costs no extra launch and overlaps with the depthwise work of the other images.
 //   wr [SQ][C] (null: no fused SE), br [SQ], we_t [SQ][C], be [C], gate [n_img][C],
 //   counters [n_img] zero on entry / zero again on exit.
-using SeArgs = DwSeArgs;
+struct SeArgs {
+  const float* wr; const float* br; const float* we_t; const float* be;
+  float* gate; int* counters; int sq; float inv_hw;
+};
 
 template <typename T, int K, int S>
 __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
@@ -592,47 +594,7 @@ int launch_dw_t(const void* in, const float* w, const float* shift, void* out, f
   return MT_ERR_UNSUPPORTED;
 }
 
-template <int K, int S>
-int launch_dw_tc_ks(const CUtensorMap& tm, const float* w, const float* shift, bf16* o, float* pool, int n_img, int H,
-                    int W, int C, const DwTcGeom& g, const SeArgs& se, cudaStream_t st) {
-  const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
-  auto kern = dwconv_tc_kernel<K, S>;
-  const size_t smem = 2 * (size_t)((g.tile_bytes + 1023) & ~1023) + (size_t)(C + se.sq) * 4 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(dwconv_tc)");
-    attr_set = true;
-  }
-  dim3 grid(g.workers, g.n_cchunks);      // persistent: each block walks images blockIdx.x, +workers, ...
-  kern<<<grid, 256, smem, st>>>(tm, w, shift, o, pool, n_img, Ho, Wo, C, same_pad_lo(H, K, S), g, se);
-  MT_LAUNCH_CHECK("dwconv_tc_kernel");
-  return MT_OK;
-}
-
-// stride-1 depthwise layers on tcgen05 (dwconv_umma.cuh): correct but 2-4x SLOWER than the mma.sync kernel
-// (each M128xN16xK16 tcgen05.mma costs ~190 cycles: it reads full 128-byte operand rows), so it is opt-in:
-// MINTIME_B200_DW=umma
-// MINTIME_B200_DW selects the bf16 depthwise kernel: (default) smem-staged FFMA2 kernel of dwconv_simt.cuh;
-// "tc" = mma.sync block-diagonal kernel, "umma" = tcgen05 variant, "simt" = register-strip kernel on global loads
-int dw_umma_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("MINTIME_B200_DW");
-    mode = 3;
-    if (e && !strcmp(e, "tc")) mode = 0;
-    if (e && !strcmp(e, "umma")) mode = 1;
-    if (e && !strcmp(e, "simt")) mode = 2;
-  }
-  return mode;
-}
-
-int device_sms() {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms > 0 ? sms : 148;
-}
+int device_sms() { return current_sms(); }
 
 template <int K, int S>
 int launch_dw_simt_ks(const CUtensorMap& tm, const float* w, const float* shift, bf16* o, float* pool, int n_img, int H,
@@ -643,12 +605,10 @@ int launch_dw_simt_ks(const CUtensorMap& tm, const float* w, const float* shift,
   static const Kern kerns[4] = {dwconv_simt_kernel<K, S, 0>, dwconv_simt_kernel<K, S, 32>, dwconv_simt_kernel<K, S, 48>,
                                 dwconv_simt_kernel<K, S, 64>};
   Kern kern = kerns[slot];
-  static bool attr_set[4] = {false, false, false, false};
-  if (!attr_set[slot]) {
+  if (first_use_on_device(reinterpret_cast<const void*>(kern))) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(dwconv_simt)");
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set[slot] = true;
   }
   // persistent blocks, statically scheduled: launch exactly as many as are co-resident (registers included),
   // so no block waits for a second wave
@@ -685,63 +645,7 @@ int launch_dw_simt(const void* in, const float* w, const float* shift, void* out
 }
 
 bool dw_simt_ok(int h, int w_, int c, int k, int s, const void* fused_se) {
-  return dw_umma_mode() == 3 && h == w_ && (k == 3 || k == 5) && (s == 1 || s == 2) && !fused_se;
-}
-
-int launch_dw_umma(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
-                   int C, int k, cudaStream_t st) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  DwUmmaGeom g = dw_umma_geom(H, W, C, k, n_img, sms > 0 ? sms : 148);
-  if (const char* e = getenv("MINTIME_B200_DW_BO")) g.use_base_offset = atoi(e);
-  const size_t smem = 2 * (size_t)g.slot_bytes + g.b_bytes + 1024;
-  MT_REQUIRE(g.IW <= 256 && g.IH <= 256 && smem <= 220 * 1024, "dwconv(umma): tile too large (%dx%d)", g.IW, g.IH);
-  CUtensorMap tm;
-  int rc = make_tmap_nhwc_bf16(&tm, in, n_img, H, W, C, g.IW, g.IH);
-  if (rc) return rc;
-  ProfScope prof(st, 2.0 * k * k * (double)n_img * H * W * C, (double)n_img * C * 2.0 * H * W * 2, "dwconv_umma k%d s1 C%d H%d",
-                 k, C, H);
-  dim3 grid(g.workers, g.n_cchunks);
-  bf16* o = reinterpret_cast<bf16*>(out);
-  const int pad = same_pad_lo(H, k, 1);
-  if (k == 3) {
-    static bool a3 = false;
-    if (!a3) { cudaFuncSetAttribute(dwconv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); a3 = true; }
-    dwconv_umma_kernel<3><<<grid, 192, smem, st>>>(tm, w, shift, o, pool, n_img, H, W, C, pad, g);
-  } else {
-    static bool a5 = false;
-    if (!a5) { cudaFuncSetAttribute(dwconv_umma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); a5 = true; }
-    dwconv_umma_kernel<5><<<grid, 192, smem, st>>>(tm, w, shift, o, pool, n_img, H, W, C, pad, g);
-  }
-  MT_LAUNCH_CHECK("dwconv_umma_kernel");
-  return MT_OK;
-}
-
-int launch_dw_tc(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
-                 int C, int k, int s, SeArgs se, cudaStream_t st) {
-  if ((k != 3 && k != 5) || (s != 1 && s != 2)) {
-    set_error("dwconv: unsupported kernel %d / stride %d", k, s);
-    return MT_ERR_UNSUPPORTED;
-  }
-  const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const DwTcGeom g = dw_tc_geom(H, W, C, k, s, n_img, sms > 0 ? sms : 148);
-  MT_REQUIRE(g.IW <= 256 && g.IH <= 256 && g.tile_bytes <= 56 * 1024, "dwconv: tile too large (%dx%d)", g.IW, g.IH);
-  CUtensorMap tm;
-  int rc = make_tmap_nhwc_bf16(&tm, in, n_img, H, W, C, g.IW, g.IH);
-  if (rc) return rc;
-  se.inv_hw = 1.0f / (float)(Ho * Wo);
-  ProfScope prof(st, 2.0 * k * k * (double)n_img * Ho * Wo * C,
-                 (double)n_img * C * ((double)H * W + (double)Ho * Wo) * 2, "dwconv_tc%s k%d s%d C%d H%d",
-                 se.wr ? "+se" : "", k, s, C, H);
-  bf16* o = reinterpret_cast<bf16*>(out);
-  if (k == 3 && s == 1) return launch_dw_tc_ks<3, 1>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
-  if (k == 3 && s == 2) return launch_dw_tc_ks<3, 2>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
-  if (k == 5 && s == 1) return launch_dw_tc_ks<5, 1>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
-  return launch_dw_tc_ks<5, 2>(tm, w, shift, o, pool, n_img, H, W, C, g, se, st);
+  return h == w_ && (k == 3 || k == 5) && (s == 1 || s == 2) && !fused_se;
 }
 
 // ---- fused expand + depthwise (mbconv_fused.cuh).  Measured on B200 at 512 images (us, fused vs expand GEMM +
@@ -783,22 +687,17 @@ int launch_front_ks(const CUtensorMap& tin, const CUtensorMap& tw, const float* 
   const int slot = g.d.CW == 32 ? 0 : (g.d.CW == 48 ? 1 : 2);
   static const Kern kerns[3] = {mbconv_front_kernel<K, S, 32>, mbconv_front_kernel<K, S, 48>, mbconv_front_kernel<K, S, 64>};
   Kern kern = kerns[slot];
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[slot]) {
+  if (first_use_on_device(reinterpret_cast<const void*>(kern))) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(mbconv_front)");
     // two ~100 KiB blocks per SM need the maximum shared-memory carve-out (the occupancy query honours it)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set[slot] = true;
   }
   const int per_sm = 1;                          // one warp-specialised block per SM (it owns all 512 TMEM columns)
   const int threads = 32 + 32 * g.nd + ((g.d.threads + 31) & ~31);
   const long long work = (long long)n_img * g.d.tiles;
   const int workers = (int)std::max(1LL, std::min(work, (long long)(device_sms() * per_sm) / g.d.n_cchunks));
   dim3 grid(workers, g.d.n_cchunks);
-  if (getenv("MINTIME_B200_DEBUG"))
-    fprintf(stderr, "mbconv_front k%d s%d: grid (%d,%d) x %d thr (%d drain warps, %d stencil thr), smem %zu, tile %dx%d in %dx%d MB %d CW %d tmem %d\n",
-            K, S, workers, g.d.n_cchunks, threads, g.nd, g.d.threads, g.smem, g.d.TH, g.d.TW, g.d.IH, g.d.IW, g.MB, g.d.CW, g.tmem_cols);
   kern<<<grid, threads, g.smem, st>>>(tin, tw, exp_shift, w_dw, dw_shift, o, pool, n_img, H, H, Ho, Ho, C,
                                           same_pad_lo(H, K, S), g);
   MT_LAUNCH_CHECK("mbconv_front_kernel");
@@ -830,7 +729,6 @@ int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
     DwSimtGeom g;
     if (dw_simt_geom(&g, h, w_, c, k, s, 1, 148)) return g.tiles;
   }
-  if (precision == MT_PREC_BF16 && dw_umma_mode() != 2) return 1;
   return dw_geom(h, w_, c, k, s).chunks;
 }
 
@@ -843,10 +741,8 @@ int dwconv_dispatch(int precision, const void* in, const float* w, const float* 
   if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
   if (precision == MT_PREC_BF16) {
     if (dw_simt_ok(h, w_, c, k, s, se.wr)) return launch_dw_simt(in, w, shift, out, pool_part, n_img, h, c, k, s, st);
-    if (dw_umma_mode() == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
-    if (s == 1 && h == w_ && (k == 3 || k == 5) && !se.wr && dw_umma_mode() == 1)
-      return launch_dw_umma(in, w, shift, out, pool_part, n_img, h, w_, c, k, st);
-    return launch_dw_tc(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+    // non-square maps / fused squeeze-excite tail: register-strip kernel on global loads
+    return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
   }
   if (precision == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);  // debug: CUDA-core bf16
   set_error("dwconv: unknown precision %d", precision);
@@ -969,11 +865,9 @@ extern "C" int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, cons
   const size_t se_smem = (size_t)kSeImgs * ((size_t)c + ((sq + 3) & ~3) + (size_t)se_jg * c) * 4;
   MT_REQUIRE(n_img > 0 && c > 0 && c % 4 == 0 && sq > 0 && sq <= 256 && hw > 0 && n_chunks > 0 && se_smem <= 200 * 1024,
              "se_gate: bad shape");
-  static bool se_attr = false;
-  if (!se_attr) {
+  if (first_use_on_device(reinterpret_cast<const void*>(se_gate_kernel))) {
     cudaError_t e = cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(se_gate)");
-    se_attr = true;
   }
   ProfScope prof(reinterpret_cast<cudaStream_t>(stream), 4.0 * n_img * (double)c * sq,
                  (double)n_img * c * 4 * (n_chunks + 1), "se_gate");

@@ -710,16 +710,7 @@ int make_tmap_2d(CUtensorMap* m, const void* base, bool f32, int rows, int cols,
   return MT_OK;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return current_sms(); }
 
 template <int KIND, bool GATED, bool TMA_OUT>
 int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
@@ -796,11 +787,9 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   }
 
   auto kern = gemm_tc_kernel<bf16, KIND, GATED, TMA_OUT>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(kern))) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc)");
-    attr_set = true;
   }
   int grid = p.tiles_m * p.tiles_n * p.splits;
   if (grid > num_sms() * ctas_per_sm) grid = num_sms() * ctas_per_sm;

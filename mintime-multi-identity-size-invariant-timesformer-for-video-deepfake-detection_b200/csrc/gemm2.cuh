@@ -269,11 +269,9 @@ int launch_tc2(const GemmArgs& g, cudaStream_t stream) {
   rc = make_tmap_2d(&tout, g.epi.out, f32, g.M, KIND == EPI_GEGLU ? g.N / 2 : g.N, g.epi.ldo, 128);
   if (rc) return rc;
   auto kern = gemm_tc2_kernel<KIND, EPI_WARPS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(kern))) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc2)");
-    attr_set = true;
   }
   int pairs = std::min(p.tiles_m * p.tiles_n, num_sms() / 2);
   cudaLaunchConfig_t cfg{};

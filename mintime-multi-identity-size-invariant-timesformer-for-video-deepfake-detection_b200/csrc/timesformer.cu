@@ -623,8 +623,12 @@ extern "C" int mt_aggregate_attn_fwd(const float* space_attn, const float* time_
 //   identity i owns slots[i] consecutive face slots, the first n_real[i] hold faces, the rest are padding
 //   size_embedding = bucket(ratio) in 1..20 for faces (SIZE_EMB_DICT, :30-31 / :259-263: (0..5)->1, (6..10)->2, ...),
 //                    0 for padding (:273-274)
-//   mask           = 1 for faces, 0 for padding when identity attention is on (:281-284), all ones otherwise
-//   padded slots repeat the identity's LAST (max) source frame number (:277), 0 when the identity has no face
+//   mask           = mask_padding ? (1 for faces, 0 for padding: predict.py:303) : all ones.  As EXECUTED,
+//                    DeepFakesDataset never masks: its second `len(identity_images) < max_faces` test (:283) sees the
+//                    list it has just padded to max_faces, so it always takes the all-ones branch (:286) -- pinned by
+//                    tests/golden/clip_meta_ref.json, generated by running the reference class.
+//   padded slots repeat the largest frame number appended SO FAR, over all identities up to this one
+//                    (`max(images_frames)` on the clip-wide list, :277 / predict.py:304); 0 when there is none yet
 //   identities_mask[q][k] = q and k belong to the same identity (:314-321)
 //   positions      = [0] + for each slot the 49 token positions (p-1)*n+1 .. p*n of p = 1-based rank of the slot's
 //                    frame number among the clip's distinct frame numbers (:323-329)
@@ -634,7 +638,7 @@ namespace mt {
 namespace {
 __global__ void __launch_bounds__(64) clip_meta_kernel(const int* __restrict__ slots, const int* __restrict__ n_real,
                                                        const int* __restrict__ frame_no, const int* __restrict__ ratio,
-                                                       int max_ids, int identity_attention, uint8_t* __restrict__ mask,
+                                                       int max_ids, int mask_padding, uint8_t* __restrict__ mask,
                                                        uint8_t* __restrict__ idmask, int* __restrict__ size_emb,
                                                        long long* __restrict__ positions, int f, int n) {
   __shared__ int ident[64], frames[64], first[64];
@@ -648,12 +652,16 @@ __global__ void __launch_bounds__(64) clip_meta_kernel(const int* __restrict__ s
       s0 += ns;
     }
     if (my_id >= 0) {
-      const int nr = n_real[b * max_ids + my_id];
-      real = j - start < nr;
+      real = j - start < n_real[b * max_ids + my_id];
       if (real) {
         fr = frame_no[b * f + j];
-      } else {                                   // padding repeats the identity's max frame number (0 if none)
-        for (int k = 0; k < nr; ++k) fr = max(fr, frame_no[b * f + start + k]);
+      } else {                                   // padding repeats the clip's largest frame number so far (0 if none)
+        int s1 = 0;
+        for (int i = 0; i <= my_id; ++i) {
+          const int nr = n_real[b * max_ids + i];
+          for (int k = 0; k < nr; ++k) fr = max(fr, frame_no[b * f + s1 + k]);
+          s1 += slots[b * max_ids + i];
+        }
       }
     }
     ident[j] = my_id;
@@ -673,7 +681,7 @@ __global__ void __launch_bounds__(64) clip_meta_kernel(const int* __restrict__ s
     bucket = r <= 5 ? 1 : min(20, (r + 4) / 5);  // (0..5)->1, (6..10)->2, ..., (96..100)->20; larger ratios clamp to 20
   }
   size_emb[b * f + j] = bucket;
-  mask[b * f + j] = (real || !identity_attention) ? 1 : 0;
+  mask[b * f + j] = (real || !mask_padding) ? 1 : 0;
   for (int k = 0; k < f; ++k) idmask[((size_t)b * f + j) * f + k] = my_id >= 0 && ident[k] == my_id;
   long long* pos = positions + (size_t)b * (1 + f * n);
   if (j == 0) pos[0] = 0;
@@ -683,14 +691,14 @@ __global__ void __launch_bounds__(64) clip_meta_kernel(const int* __restrict__ s
 }  // namespace mt
 
 extern "C" int mt_clip_meta_fwd(const int32_t* slots, const int32_t* n_real, const int32_t* frame_no, const int32_t* ratio,
-                                int max_identities, int identity_attention, uint8_t* mask, uint8_t* identities_mask,
+                                int max_identities, int mask_padding, uint8_t* mask, uint8_t* identities_mask,
                                 int32_t* size_embedding, int64_t* positions, int batch, int f, int n_patches, void* stream) {
   MT_REQUIRE(slots && n_real && frame_no && ratio && mask && identities_mask && size_embedding && positions,
              "clip_meta: null pointer");
   MT_REQUIRE(batch > 0 && f >= 1 && f <= 64 && n_patches >= 1 && max_identities >= 1, "clip_meta: bad shape B=%d f=%d n=%d ids=%d",
              batch, f, n_patches, max_identities);
   mt::clip_meta_kernel<<<batch, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      slots, n_real, frame_no, ratio, max_identities, identity_attention, mask, identities_mask, size_embedding,
+      slots, n_real, frame_no, ratio, max_identities, mask_padding, mask, identities_mask, size_embedding,
       reinterpret_cast<long long*>(positions), f, n_patches);
   MT_LAUNCH_CHECK("clip_meta_kernel");
   return MT_OK;

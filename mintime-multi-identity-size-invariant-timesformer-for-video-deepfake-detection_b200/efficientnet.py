@@ -112,6 +112,10 @@ class EfficientNet(nn.Module):
         self._packed = None
         return super()._load_from_state_dict(*a, **k)
 
+    def load_state_dict(self, state_dict, *a, **k):
+        """Also accepts 'module.'-prefixed (``nn.DataParallel``) checkpoints (predict.py:375-388) on the bare module."""
+        return super().load_state_dict(weights._strip(state_dict), *a, **k)
+
     def _apply(self, fn, *a, **k):
         self._packed = None
         return super()._apply(fn, *a, **k)

@@ -133,6 +133,11 @@ class SizeInvariantTimeSformer(nn.Module):
         self._packed = None
         return super()._load_from_state_dict(*a, **k)
 
+    def load_state_dict(self, state_dict, *a, **k):
+        """Also accepts a checkpoint saved from ``nn.DataParallel(model)`` ('module.' prefix: train.py:461-464 saves
+        them, predict.py:375-386 loads them into a wrapped model) directly into the bare module."""
+        return super().load_state_dict(weights._strip(state_dict), *a, **k)
+
     def _apply(self, fn, *a, **k):
         self._packed = None
         return super()._apply(fn, *a, **k)

@@ -144,9 +144,11 @@ def make_clip_meta(num_frames: int, n_identities: int, rng: np.random.Generator,
                    num_patches: int = 49) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
     """(size_emb[f] i32, mask[f] bool, identities_mask[f,f] bool, positions[1+f*n] i64) for one video.
 
-    deepfakes_dataset.py:259-263 (size bucket 1..20, 0 on padded slots), :273-287 (mask),
-    :314-321 (block-diagonal identities mask), :323-329 (positions = rank of the source frame among
-    the video's distinct frames; padded slots repeat the identity's last frame).
+    A synthetic INPUT generator shaped like predict.py generate_masks (:254-352): size bucket 1..20, 0 on padded
+    slots; mask 0 on padded slots; block-diagonal identities mask; positions = rank of the source frame among the
+    video's distinct frames.  (Padded slots repeat the identity's own last frame here; the executed reference repeats
+    the clip-wide maximum so far -- the builder that reproduces the reference exactly is utils.build_clip_meta, pinned
+    by tests/golden/clip_meta_ref.json.  The golden model fixtures were generated from THIS generator's tensors.)
     """
     f = num_frames
     slots = identity_slots(f, n_identities)

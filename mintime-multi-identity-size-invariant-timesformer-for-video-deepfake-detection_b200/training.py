@@ -308,8 +308,9 @@ class TsfTrainFunction(torch.autograd.Function):
         # ---- token build (:225-248)
         g3 = g.view(B, N, dim)
         rows = model.pos_emb.weight.shape[0]
-        dpos, dsize, dcls = ops.embed_bwd(g3, pos, se, rows, f, n, want_pos=bool(model.enable_pos_emb),
-                                          want_size=bool(model.enable_size_emb))
+        # pos_emb trains in BOTH modes: with enable-pos-emb off the reference still adds pos_emb(arange(N))
+        # (size_invariant_timesformer.py:237-238); `pos` is None then and the kernel scatters to rows 0..N-1
+        dpos, dsize, dcls = ops.embed_bwd(g3, pos, se, rows, f, n, want_pos=True, want_size=bool(model.enable_size_emb))
         Mt = B * f * n
         _, _, cs = ops.grad_prep(g, want_colsum=True, rows_per_batch=f * n, m=Mt, precision=precision)
         dwp = torch.zeros((dim, model.channels), dtype=f32, device=dev)
@@ -321,7 +322,7 @@ class TsfTrainFunction(torch.autograd.Function):
             sync.launch(prev[0])
         grads["to_patch_embedding.weight"], grads["to_patch_embedding.bias"] = dwp, cs
         grads["cls_token"] = dcls.view(1, dim)
-        grads["pos_emb.weight"] = dpos if dpos is not None else torch.zeros_like(model.pos_emb.weight)
+        grads["pos_emb.weight"] = dpos
         if model.enable_size_emb:
             grads["size_emb.weight"] = dsize
         if sync is not None:

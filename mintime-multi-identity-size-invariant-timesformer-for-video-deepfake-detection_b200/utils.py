@@ -55,14 +55,18 @@ def aggregate_attentions(attentions, heads, num_frames, frames_per_identity, sca
 
 
 def build_clip_meta(slots: torch.Tensor, n_real: torch.Tensor, frame_no: torch.Tensor, ratio: torch.Tensor,
-                    num_patches: int = 49, identity_attention: bool = True):
+                    num_patches: int = 49, source: str = "predict"):
     """mask / identities_mask / size_embedding / positions of a batch of clips, assembled on the device
     (mt_clip_meta_fwd) from the per-identity slot table -- what ``DeepFakesDataset.__getitem__``
     (deepfakes_dataset.py:259-330) and predict.py's ``generate_masks`` build per clip on the host.
 
+    ``source`` picks which of the reference's two assemblies is reproduced: "predict" (generate_masks: padded slots
+    get mask 0) or "dataset" (DeepFakesDataset as executed: the mask is all ones, see csrc/timesformer.cu).
     slots, n_real: int32 (B, max_identities); frame_no, ratio: int32 (B, f); all on the same CUDA device.
     Returns a dict with the tensors ``SizeInvariantTimeSformer.forward`` takes: mask bool (B,f), identities_mask
     bool (B,f,f), size_embedding int32 (B,f), positions int64 (B, 1+f*num_patches)."""
+    if source not in ("predict", "dataset"):
+        raise ValueError("source must be 'predict' or 'dataset'")
     dev = slots.device
     _lib.require_device(dev)
     for t in (slots, n_real, frame_no, ratio):
@@ -76,7 +80,7 @@ def build_clip_meta(slots: torch.Tensor, n_real: torch.Tensor, frame_no: torch.T
     pos = torch.empty((b, 1 + f * num_patches), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.load().mt_clip_meta_fwd(slots.data_ptr(), n_real.data_ptr(), frame_no.data_ptr(), ratio.data_ptr(), ids,
-                                          1 if identity_attention else 0, mask.data_ptr(), idm.data_ptr(), se.data_ptr(),
+                                          1 if source == "predict" else 0, mask.data_ptr(), idm.data_ptr(), se.data_ptr(),
                                           pos.data_ptr(), b, f, num_patches, _lib.stream_ptr())
     _lib.check(rc, "mt_clip_meta_fwd")
     return {"mask": mask.view(torch.bool), "identities_mask": idm.view(torch.bool), "size_embedding": se, "positions": pos}

@@ -2,10 +2,11 @@
 never by the product path).
 
 Follows ``DeepFakesDataset.__getitem__`` (deepfakes_dataset.py:259-330) and predict.py ``generate_masks`` (:254-352)
-statement by statement, with the file reads replaced by in-memory (frame number, area ratio) pairs.  PARITY UNPINNED
-against an executed reference: the dataset class needs albumentations / python-magic / image files and cannot run in
-this container, and the reference ships no fixture for it; the known-answer case in tests/test_host_logic.py is
-worked out by hand from the cited lines.
+statement by statement, with the file reads replaced by in-memory (frame number, area ratio) pairs, and
+``aggregate_attentions`` (utils.py:68-86).  PINNED against the executed reference: oracle/make_golden_clip_meta.py cuts
+the reference's ``DeepFakesDataset`` class / ``aggregate_attentions`` function out of their source files, runs them
+unmodified (synthetic on-disk clips; only the augmentation pipeline is replaced) and stores inputs + outputs in
+tests/golden/clip_meta_ref.json / aggregate_attn_ref.npz; tests/test_oracle.py holds this file to them.
 """
 from __future__ import annotations
 
@@ -18,9 +19,10 @@ SIZE_EMB_DICT = [(1 + i * RANGE_SIZE, (i + 1) * RANGE_SIZE) if i != 0 else (0, R
 
 
 def clip_meta(identities: Sequence[Tuple[int, List[Tuple[int, int]]]], num_frames: int, num_patches: int = 49,
-              enable_identity_attention: bool = True):
+              enable_identity_attention: bool = True, source: str = "dataset"):
     """identities: [(max_faces, [(frame_number, ratio), ...faces read for this identity]), ...] with sum(max_faces) ==
-    num_frames.  Returns (size_embeddings[f] int32, mask[f] bool, identities_mask[f][f] bool, positions[1+f*n] int64)."""
+    num_frames.  Returns (size_embeddings[f] int32, mask[f] bool, identities_mask[f][f] bool, positions[1+f*n] int64).
+    source = "dataset": DeepFakesDataset.__getitem__; "predict": predict.py generate_masks (masks the padded slots)."""
     mask: List[int] = []
     size_embeddings: List[float] = []
     images_frames: List[int] = []
@@ -36,9 +38,18 @@ def clip_meta(identities: Sequence[Tuple[int, List[Tuple[int, int]]]], num_frame
         if n_read < max_faces:                                                                     # :273
             diff = max_faces - len(identity_size_embeddings)
             identity_size_embeddings = list(identity_size_embeddings) + [0] * diff                 # :275
-            own = images_frames[len(images_frames) - n_read:] if n_read else []
-            images_frames.extend([max(own) if own else 0 for _ in range(diff)])                    # :277-281
-        if enable_identity_attention and n_read < max_faces:                                       # :283
+            # max over the CLIP-wide list (earlier identities included); empty list -> 0 (the except branch)
+            images_frames.extend([max(images_frames) if images_frames else 0 for _ in range(diff)])   # :277-281
+            n_images = max_faces                   # identity_images.extend(...) (:276): the list is full from here on
+        else:
+            n_images = n_read
+        if source == "predict":
+            masked = n_read < max_faces            # predict.py:300-306: the mask is built inside the padding branch
+        else:
+            # :283 re-tests len(identity_images) AFTER :276 padded it, so as executed this is never true and
+            # DeepFakesDataset always returns an all-ones mask, whatever enable_identity_attention says
+            masked = enable_identity_attention and n_images < max_faces
+        if masked:
             mask.extend([1 if i < max_faces - diff else 0 for i in range(max_faces)])              # :284
         else:
             mask.extend([1 for _ in range(max_faces)])                                             # :286
@@ -57,3 +68,20 @@ def clip_meta(identities: Sequence[Tuple[int, List[Tuple[int, int]]]], num_frame
     positions.insert(0, 0)                                                                         # :329
     return (np.asarray(size_embeddings, np.int32), np.asarray(mask, bool), np.asarray(identities_mask, bool),
             np.asarray(positions, np.int64))
+
+
+def aggregate_attentions(attentions, heads: int, num_frames: int, scale_factor: float = 50000.0):
+    """utils.py:68-86 for one video: attentions = [space, time], each (heads, 1, N) float arrays.
+    Returns (3, num_frames) float64: softmaxed per-frame attention of space, time, space + time."""
+    aggregated = []
+    for attention in attentions:
+        a = np.asarray(attention, np.float64).reshape(-1, heads, np.asarray(attention).shape[-1])   # '(b h) t -> b h t' (:74)
+        aggregated.append([a[:, :, i].max() for i in range(a.shape[2])])                             # :75
+    aggregated.append(list(np.sum(np.asarray(aggregated), axis=0)))                                  # :79
+    out = []
+    for lst in aggregated:                                                                           # :83-85
+        chunks = np.array_split(np.asarray(lst), num_frames)
+        v = np.asarray([float(np.mean(c)) * scale_factor for c in chunks], np.float64)
+        e = np.exp(v - v.max())                                                                      # scipy softmax
+        out.append(e / e.sum())
+    return np.stack(out)

@@ -180,19 +180,22 @@ def test_patch_embed_tokens(prec):
 
 
 def _ref_aggregate(attentions, heads, num_frames, scale_factor=50000):
-    """reference utils.py:68-86 restated with numpy (single video)."""
-    agg = []
-    for a in attentions:
-        a = a.squeeze(1).reshape(-1, heads, a.shape[-1]).numpy()
-        agg.append([a[:, :, i].max() for i in range(a.shape[2])])
-    agg.append(list(np.sum(np.asarray(agg), axis=0)))
-    out = []
-    for lst in agg:
-        chunks = np.array_split(np.asarray(lst), num_frames)
-        v = np.array([c.mean() * scale_factor for c in chunks], dtype=np.float64)
-        e = np.exp(v - v.max())
-        out.append(e / e.sum())
-    return out
+    """the pinned oracle of utils.py:68-86 (oracle/clip_meta_oracle.py, single video)"""
+    from oracle.clip_meta_oracle import aggregate_attentions as agg
+    return list(agg([a.numpy() for a in attentions], heads, num_frames, scale_factor))
+
+
+def test_aggregate_attentions_matches_executed_reference():
+    """mt_aggregate_attn_fwd on the inputs of tests/golden/aggregate_attn_ref.npz, whose outputs were produced by
+    the reference's own aggregate_attentions (oracle/make_golden_clip_meta.py)."""
+    from mintime_b200.utils import aggregate_attentions_batched
+    g = load_golden("aggregate_attn_ref")
+    for n in sorted(k[:-4] for k in g if k.endswith(".out")):
+        heads, f, N, scale = (int(v) for v in g[n + ".meta"])
+        maps = [torch.from_numpy(g[n + ".space_in"]).to(DEV), torch.from_numpy(g[n + ".time_in"]).to(DEV)]
+        out = aggregate_attentions_batched(maps, heads, f, scale_factor=scale).cpu().numpy()
+        # fp32 on the device against the reference's float64: scale 50000 amplifies the mean's rounding
+        np.testing.assert_allclose(out[0], g[n + ".out"], rtol=5e-3 if scale > 1000 else 2e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("f", [8, 16])
@@ -579,17 +582,45 @@ def test_clip_meta_on_device(f, max_ids):
             frame_no[b, start + nr:start + ns] = 777          # garbage in padded slots must be ignored
             ids.append((int(ns), [(int(a), int(c)) for a, c in zip(fr, ra)]))
             start += ns
-        want.append(clip_meta(ids, f))
-    for ia in (True, False):
+        want.append(clip_meta(ids, f, source="predict"))
+    for src in ("predict", "dataset"):
         out = build_clip_meta(torch.from_numpy(slots).to(DEV), torch.from_numpy(n_real).to(DEV),
-                              torch.from_numpy(frame_no).to(DEV), torch.from_numpy(ratio).to(DEV), identity_attention=ia)
+                              torch.from_numpy(frame_no).to(DEV), torch.from_numpy(ratio).to(DEV), source=src)
         torch.cuda.synchronize()
         for b in range(B):
             se, mask, idm, pos = want[b]
             assert (out["size_embedding"][b].cpu().numpy() == se).all()
-            assert (out["mask"][b].cpu().numpy() == (mask if ia else np.ones_like(mask))).all()
+            assert (out["mask"][b].cpu().numpy() == (mask if src == "predict" else np.ones_like(mask))).all()
             assert (out["identities_mask"][b].cpu().numpy() == idm).all()
             assert (out["positions"][b].cpu().numpy() == pos).all()
+
+
+@pytest.mark.gpu
+def test_clip_meta_on_device_matches_executed_reference():
+    """mt_clip_meta_fwd on the slot tables of tests/golden/clip_meta_ref.json: the expected tensors were produced by
+    the reference's own DeepFakesDataset.__getitem__ (oracle/make_golden_clip_meta.py).  Bit exact."""
+    import json
+    import os
+    from helpers import GOLDEN_DIR
+    from mintime_b200.utils import build_clip_meta
+    cases = json.load(open(os.path.join(GOLDEN_DIR, "clip_meta_ref.json")))
+    for name, c in cases.items():
+        f, ids = c["num_frames"], c["identities"]
+        slots = np.zeros((1, len(ids)), np.int32); n_real = np.zeros((1, len(ids)), np.int32)
+        frame_no = np.full((1, f), 12345, np.int32); ratio = np.zeros((1, f), np.int32)
+        start = 0
+        for i, (mf, faces) in enumerate(ids):
+            slots[0, i] = mf; n_real[0, i] = len(faces)
+            for j, (fr, ra) in enumerate(faces):
+                frame_no[0, start + j] = fr; ratio[0, start + j] = ra
+            start += mf
+        out = build_clip_meta(torch.from_numpy(slots).to(DEV), torch.from_numpy(n_real).to(DEV),
+                              torch.from_numpy(frame_no).to(DEV), torch.from_numpy(ratio).to(DEV),
+                              num_patches=c["num_patches"], source=c["source"])
+        assert out["size_embedding"][0].cpu().tolist() == c["size_embedding"], name
+        assert out["mask"][0].cpu().int().tolist() == c["mask"], name
+        assert out["identities_mask"][0].cpu().int().tolist() == c["identities_mask"], name
+        assert out["positions"][0].cpu().tolist() == c["positions"], name
 
 
 @pytest.mark.gpu

@@ -247,6 +247,29 @@ def test_backward_matches_reference_gradients(prec, case):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("switch", ["enable-pos-emb", "enable-size-emb"])
+def test_backward_with_an_embedding_switched_off(switch):
+    """enable-pos-emb: False still adds pos_emb(arange(N)) (size_invariant_timesformer.py:237-238), so the table keeps
+    training; enable-size-emb: False drops the size table.  fp32 path vs the oracle differentiated by torch autograd."""
+    cfg, tsd, meta, feats, labels, pw = grad_case_inputs("b3_f16_mixed_d2")
+    cfg = copy.deepcopy(cfg)
+    cfg["model"][switch] = False
+    tsd = {k: v for k, v in tsd.items() if cfg["model"]["enable-size-emb"] or not k.startswith("size_emb")}
+    model = SizeInvariantTimeSformer(config=cfg, precision="fp32")
+    model.load_state_dict(tsd)
+    model = model.to(DEV).train()
+    y, loss = _step(model, cfg, meta, feats.to(DEV), labels, pw)
+    loss.backward()
+    osd = {k: v.clone().requires_grad_(True) for k, v in tsd.items()}
+    ol, _ = orc.tsf_forward(osd, cfg, feats, meta["mask"], meta["identities_mask"], meta["size_embedding"], meta["positions"])
+    torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw]))(ol, labels).backward()
+    assert (y.detach().cpu() - ol.detach()).abs().max() <= 2e-4
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert float(osd[k].grad.norm()) > 0, k
+        assert rel_err(p.grad.cpu(), osd[k].grad) <= 2e-3, k
+
+
 def test_sgd_loss_curve_matches_oracle():
     """4 SGD steps (config: lr 0.01, weight decay 1e-4, train.py:266-268) on the same batch: CUDA fp32 path vs the
     oracle differentiated by torch autograd on the host."""

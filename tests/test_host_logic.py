@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.mt_abi_version.restype = ctypes.c_int
-    assert lib.mt_abi_version() == 3
+    assert lib.mt_abi_version() == 4
     lib.mt_last_error.restype = ctypes.c_char_p
     assert lib.mt_last_error() == b""
 
@@ -67,6 +67,28 @@ def test_load_matching_state_dict_semantics():
     renamed["some.unknown.key"] = torch.zeros(3)
     m.load_matching_state_dict(renamed)               # model.py:368-378
     assert torch.equal(m.state_dict()["_blocks.3._project_conv.weight"], sd["_blocks.3._project_conv.weight"])
+
+
+def test_module_prefixed_checkpoints_load_like_predict_py():
+    """predict.py:375-388 wraps both modules in nn.DataParallel and loads checkpoints whose keys carry 'module.'
+    (train.py:461-464 saves the wrapped modules).  Both routes work: into the wrapper, and into the bare module."""
+    cfg = spec.default_tsf_config(num_frames=8)
+    sd = synth.make_tsf_state_dict(cfg, 5)
+    pref = {"module." + k: v for k, v in sd.items()}
+    bare = SizeInvariantTimeSformer(config=cfg)
+    res = bare.load_state_dict(pref)                            # strict
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(bare.state_dict()["layers.3.1.fn.to_qkv.weight"], sd["layers.3.1.fn.to_qkv.weight"])
+    wrapped = torch.nn.DataParallel(SizeInvariantTimeSformer(config=cfg))
+    wrapped.load_state_dict(pref)
+    assert torch.equal(wrapped.module.state_dict()["to_out.1.weight"], sd["to_out.1.weight"])
+    assert set(wrapped.state_dict()) == set(pref)
+    esd = synth.make_effnet_state_dict(6)
+    ext = EfficientNet.from_name("efficientnet-b0")
+    ext.load_state_dict({"module." + k: v for k, v in esd.items()})
+    assert torch.equal(ext.state_dict()["_blocks.7._bn1.running_var"], esd["_blocks.7._bn1.running_var"])
+    with pytest.raises(RuntimeError):                           # strict loading still rejects foreign keys
+        bare.load_state_dict({**pref, "module.nope": torch.zeros(1)})
 
 
 def test_tsf_state_dict_matches_reference_names():
@@ -192,21 +214,23 @@ def test_synthetic_clip_metadata_contract():
 
 
 def test_clip_meta_oracle_known_answer():
-    """Hand-worked case of deepfakes_dataset.py:259-330: f=8, identity A owns 4 slots with 4 faces, identity B owns 4
-    slots with 2 faces (2 padded slots repeat B's last frame, get size 0 and mask 0)."""
+    """The case tests/golden/clip_meta_ref.json holds as 'two_ids_padded_f8' (outputs of the executed reference), with
+    2 patches per frame: f=8, identity A owns 4 slots with 4 faces, identity B owns 4 slots with 2 faces; the 2 padded
+    slots repeat the CLIP's largest frame so far (12, not B's own 9), get size 0, and mask 0 only in predict.py."""
     from oracle.clip_meta_oracle import clip_meta
     ids = [(4, [(3, 0), (5, 5), (9, 6), (12, 100)]), (4, [(5, 17), (9, 50)])]
-    se, mask, idm, pos = clip_meta(ids, 8, num_patches=2)
+    se, mask, idm, pos = clip_meta(ids, 8, num_patches=2, source="predict")
     assert se.tolist() == [1, 1, 2, 20, 4, 10, 0, 0]
     assert mask.tolist() == [True] * 6 + [False] * 2
     assert idm[:4, :4].all() and idm[4:, 4:].all() and not idm[:4, 4:].any() and not idm[4:, :4].any()
-    # distinct frames sorted: 3, 5, 9, 12 -> ranks 1..4; slots: 3,5,9,12 | 5,9,9,9
-    ranks = [1, 2, 3, 4, 2, 3, 3, 3]
+    # distinct frames sorted: 3, 5, 9, 12 -> ranks 1..4; slots: 3,5,9,12 | 5,9,12,12
+    ranks = [1, 2, 3, 4, 2, 3, 4, 4]
     want = [0] + [t for r in ranks for t in ((r - 1) * 2 + 1, (r - 1) * 2 + 2)]
     assert pos.tolist() == want
-    # identity attention off: every slot valid (deepfakes_dataset.py:285-286)
-    _, mask2, _, _ = clip_meta(ids, 8, num_patches=2, enable_identity_attention=False)
-    assert mask2.all()
+    # DeepFakesDataset as executed: every slot valid, whatever enable_identity_attention says (:283 vs :276)
+    for ia in (True, False):
+        se2, mask2, _, pos2 = clip_meta(ids, 8, num_patches=2, enable_identity_attention=ia, source="dataset")
+        assert mask2.all() and se2.tolist() == se.tolist() and pos2.tolist() == want
 
 
 def test_clip_meta_oracle_agrees_with_synthetic_generator():
@@ -226,5 +250,9 @@ def test_clip_meta_oracle_agrees_with_synthetic_generator():
             faces = [(ranks[start + i] * 10, int(se[start + i]) * 5) for i in range(real)]   # ratio 5*b -> bucket b
             ids.append((ns, faces))
             start += ns
-        se2, mask2, idm2, pos2 = clip_meta(ids, 16)
-        assert (se2 == se).all() and (mask2 == mask).all() and (idm2 == idm).all() and (pos2 == pos).all()
+        se2, mask2, idm2, pos2 = clip_meta(ids, 16, source="predict")
+        assert (se2 == se).all() and (mask2 == mask).all() and (idm2 == idm).all()
+        # positions agree on every slot that holds a face (the generator pads with the identity's own last frame, the
+        # executed reference with the clip-wide maximum so far: tests/golden/clip_meta_ref.json)
+        real_tok = np.concatenate(([True], np.repeat(mask, 49)))
+        assert (pos2[real_tok] == pos[real_tok]).all()
