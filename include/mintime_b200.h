@@ -74,6 +74,8 @@ typedef struct {
   const float* ln_g; const float* ln_b;    /* PreNorm LayerNorm            size_invariant_timesformer.py:18-26 */
   const void* w_qkv;                       /* T [3*inner][dim], q rows pre-scaled by dim_head^-0.5 (:114) */
   const void* w_out; const float* b_out;   /* T [dim][inner], f32 [dim]                                   (:103-106) */
+  const void* w_qkv_heads;                 /* bf16 [heads][3*dim_head][dim]: the rows of w_qkv regrouped per head (q | k | v
+                                            * of head h contiguous) for the fused attention kernel; NULL = unfused path */
 } mt_attn_weights_t;
 
 typedef struct {
@@ -197,6 +199,20 @@ int mt_expand_dwconv_fwd(const void* in, const void* w_exp, const float* exp_shi
 int mt_clip_meta_fwd(const int32_t* slots, const int32_t* n_real, const int32_t* frame_no, const int32_t* ratio,
                      int max_identities, int mask_padding, uint8_t* mask, uint8_t* identities_mask,
                      int32_t* size_embedding, int64_t* positions, int batch, int f, int n_patches, void* stream);
+
+/* Attention.forward up to the head merge (:109-141) in ONE kernel, bf16 only: per-head QKV projection of the
+ * LayerNorm'd tokens on tcgen05 (CTA pairs, the 128-token tile resident in shared memory, W streamed per head) ->
+ * identity-masked softmax(QK^T)V on the tiles in shared memory -> out.  qkv never goes to HBM.
+ *   xn bf16 [B][1+f*n][dim] (the PreNorm output), w_qkv_heads as in mt_attn_weights_t, mask / identities_mask / mode /
+ *   out / cls_attn as in mt_divided_attn_fwd.  workspace: mt_fused_attn_workspace_bytes(...), 256-byte aligned.
+ * mt_fused_attn_supported() tells whether a shape has a fused schedule (dim 512, dim_head 64, f in {8,16,32}, n <= 55);
+ * mt_fused_attn_fwd returns MT_ERR_UNSUPPORTED otherwise and mt_tsf_fwd falls back to LayerNorm -> mt_pointwise_fwd ->
+ * mt_divided_attn_fwd. */
+int mt_fused_attn_supported(int f, int n, int heads, int dim_head, int dim);
+size_t mt_fused_attn_workspace_bytes(int batch, int f, int n, int heads);
+int mt_fused_attn_fwd(const void* xn, const void* w_qkv_heads, const uint8_t* mask, const uint8_t* identities_mask,
+                      int mode, void* out, float* cls_attn, int batch, int f, int n, int heads, int dim_head, int dim,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stem: ZeroPad2d(0,1,0,1) + conv 3x3 s2 (3->32) + BN + swish (utils.py:248-276, model.py:276)
  *   x NHWC [n_img][H][W][3] (f32/u8) -> out T NHWC [n_img][H/2][W/2][32] */

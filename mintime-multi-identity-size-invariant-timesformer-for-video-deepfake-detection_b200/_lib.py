@@ -20,7 +20,8 @@ EXPORTS = [
     "mt_abi_version", "mt_last_error", "mt_device_check",
     "mt_effnet_b0_workspace_bytes", "mt_effnet_b0_fwd", "mt_tsf_workspace_bytes", "mt_tsf_fwd",
     "mt_pointwise_fwd", "mt_linear_residual_fwd", "mt_linear_geglu_fwd", "mt_patch_embed_fwd",
-    "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
+    "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_fused_attn_supported",
+    "mt_fused_attn_workspace_bytes", "mt_fused_attn_fwd", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
     "mt_dwconv_chunks", "mt_dwconv_se_fwd", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
     "mt_aggregate_attn_fwd", "mt_clip_meta_fwd",
     "mt_grad_prep_workspace_bytes", "mt_grad_prep", "mt_linear_wgrad", "mt_colsum_f32", "mt_layernorm_bwd_workspace_bytes", "mt_layernorm_bwd",
@@ -45,7 +46,7 @@ class EffnetWeights(C.Structure):
 
 
 class AttnWeights(C.Structure):
-    _fields_ = [("ln_g", fp), ("ln_b", fp), ("w_qkv", vp), ("w_out", vp), ("b_out", fp)]
+    _fields_ = [("ln_g", fp), ("ln_b", fp), ("w_qkv", vp), ("w_out", vp), ("b_out", fp), ("w_qkv_heads", vp)]
 
 
 class FFWeights(C.Structure):
@@ -103,6 +104,11 @@ def load() -> C.CDLL:
     lib.mt_divided_attn_fwd.argtypes = [i32, vp, vp, vp, i32, vp, fp, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.mt_divided_attn_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.mt_divided_attn_workspace_bytes.restype = sz
+    lib.mt_fused_attn_supported.argtypes = [i32, i32, i32, i32, i32]
+    lib.mt_fused_attn_supported.restype = i32
+    lib.mt_fused_attn_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.mt_fused_attn_workspace_bytes.restype = sz
+    lib.mt_fused_attn_fwd.argtypes = [vp, vp, vp, vp, i32, vp, fp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.mt_stem_fwd.argtypes = [i32, vp, i32, fp, fp, vp, i32, i32, i32, vp]
     lib.mt_dwconv_fwd.argtypes = [i32, vp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_se_gate_fwd.argtypes = [fp, i32, i32, fp, fp, fp, fp, fp, i32, i32, i32, vp]

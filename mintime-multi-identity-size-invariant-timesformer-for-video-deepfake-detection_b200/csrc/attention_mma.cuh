@@ -306,14 +306,16 @@ __device__ __forceinline__ void cls_partial_warp(uint8_t* ks, uint8_t* vs, const
 // Merge of the per-group partials with the CLS key itself; one block (64 threads) per (b, h).
 // Writes the CLS row of `out` and, when `cls_attn` is given (it holds the raw scores of the patch keys),
 // normalises it in place into the attention map the model returns (:271).
-static __global__ void __launch_bounds__(64) cls_combine_kernel(const bf16* __restrict__ qkv, const float* __restrict__ parts,
-                                                                bf16* __restrict__ out, float* __restrict__ cls_attn,
-                                                                int N, int G, int heads) {
+// `qkv_rows` = rows per video of the buffer `qkv` points at: N for the full qkv tensor, 1 for the fused kernel's
+// compact [B][3*inner] copy of the CLS token's q, k, v.
+static __global__ void __launch_bounds__(64) cls_combine_kernel(const bf16* __restrict__ qkv, int qkv_rows,
+                                                                const float* __restrict__ parts, bf16* __restrict__ out,
+                                                                float* __restrict__ cls_attn, int N, int G, int heads) {
   __shared__ float red[2];
   __shared__ __align__(16) float ps[64 * kClsStride];            // the (b, h)'s partials (G <= 63)
   const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
   const int inner = heads * 64, ld = 3 * inner;
-  const bf16* base = qkv + (size_t)b * N * ld + h * 64;
+  const bf16* base = qkv + (size_t)b * qkv_rows * ld + h * 64;
   const int d = threadIdx.x;
   {                                              // all loads independent: one L2 round trip, not one per group
     const float2* src = reinterpret_cast<const float2*>(parts + (size_t)bh * G * kClsStride);

@@ -221,5 +221,7 @@ int make_tmap_nhwc_bf16(CUtensorMap_st* m, const void* base, int n, int h, int w
 int make_tmap_nhwc_bf16_kmajor(CUtensorMap_st* m, const void* base, int n, int h, int w, int c, int box_c, int box_w,
                                int box_h);
 int make_tmap_weights_kmajor(CUtensorMap_st* m, const void* base, int rows, int cols, int box_rows, int box_cols);
+int make_tmap_4d_bf16_sw128(CUtensorMap_st* m, const void* base, const unsigned long long dims[4],
+                            const unsigned long long strides[3], const unsigned box[4]);
 
 }  // namespace mt

@@ -892,6 +892,29 @@ int make_tmap_weights_kmajor(CUtensorMap_st* m, const void* base, int rows, int 
   return make_tmap_2d(m, base, false, rows, cols, cols, box_rows, box_cols * 2);
 }
 
+// generic 4-D bf16 map, 128-byte swizzle: dims / box innermost first, strides (bytes) of dims 1..3
+int make_tmap_4d_bf16_sw128(CUtensorMap_st* m, const void* base, const unsigned long long dims[4],
+                            const unsigned long long strides[3], const unsigned box[4]) {
+  auto enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return MT_ERR_DRIVER;
+  }
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides[0], strides[1], strides[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d) dims %llu %llu %llu %llu box %u %u %u %u base=%p", (int)r, dims[0],
+              dims[1], dims[2], dims[3], box[0], box[1], box[2], box[3], base);
+    return MT_ERR_DRIVER;
+  }
+  return MT_OK;
+}
+
 int make_tmap_nhwc_bf16_plain(CUtensorMap_st* m, const void* base, int n, int h, int w, int c, int box_c, int box_w,
                               int box_h) {
   auto enc = get_encode_fn();

@@ -3,7 +3,9 @@
 // with the identity mask, the CLS-row attention, token assembly for the CLS row, the head, and the
 // layer schedule.  Residual stream x is fp32 [B][1+f*n][dim]; GEMM operands are T.
 #include <float.h>
+#include <stdlib.h>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "attention_mma.cuh"
@@ -319,7 +321,7 @@ int launch_attn_t(const void* qkv, const uint8_t* mask, const uint8_t* idmask, i
   if constexpr (std::is_same<T, bf16>::value) {
     // bf16 path: warp-level tensor-core kernels (attention_mma.cuh)
     auto combine = [&]() -> int {
-      attn::cls_combine_kernel<<<B * heads, 64, 0, st>>>(q, cls_parts, o, cls_attn, N, mode == MT_ATTN_SPACE ? f : n, heads);
+      attn::cls_combine_kernel<<<B * heads, 64, 0, st>>>(q, N, cls_parts, o, cls_attn, N, mode == MT_ATTN_SPACE ? f : n, heads);
       MT_LAUNCH_CHECK("cls_combine_kernel");
       return MT_OK;
     };
@@ -361,7 +363,7 @@ size_t attn_ws_bytes(int B, int f, int n, int heads) {
   return (size_t)B * heads * (size_t)std::max(f, n) * attn::kClsStride * sizeof(float);
 }
 
-struct TsfWs { size_t x, xn, qkv, o, h, cls, total; };
+struct TsfWs { size_t x, xn, qkv, o, h, cls, total; };   // cls: CLS-row partials (+ the fused kernel's CLS q/k/v copy)
 TsfWs tsf_ws_layout(const mt_tsf_cfg_t& c, int B, int precision) {
   const size_t es = precision == MT_PREC_FP32 ? 4 : 2;
   const size_t rows = (size_t)B * (1 + (size_t)c.num_frames * c.num_patches);
@@ -373,9 +375,19 @@ TsfWs tsf_ws_layout(const mt_tsf_cfg_t& c, int B, int precision) {
   l.qkv = off; off += align_up(rows * 3 * inner * es, 1024);
   l.o = off;   off += align_up(rows * inner * es, 1024);
   l.h = off;   off += align_up(rows * 4 * c.dim * es, 1024);
-  l.cls = off; off += align_up(attn_ws_bytes(B, c.num_frames, c.num_patches, c.heads), 1024);
+  l.cls = off; off += align_up(std::max(attn_ws_bytes(B, c.num_frames, c.num_patches, c.heads),
+                                        mt_fused_attn_workspace_bytes(B, c.num_frames, c.num_patches, c.heads)), 1024);
   l.total = off;
   return l;
+}
+
+// MINTIME_B200_FUSED_ATTN=0 (read once) keeps the unfused projection + attention kernels: A/B measurements
+bool fused_attn_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MINTIME_B200_FUSED_ATTN");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int check_cfg(const mt_tsf_cfg_t* c) {
@@ -541,11 +553,19 @@ extern "C" int mt_tsf_fwd(const mt_tsf_weights_t* w, const mt_tsf_cfg_t* cfg, co
       float* amap = !last ? nullptr : (mode == 0 ? time_attn : space_attn);
       rc = mt_layernorm_fwd(precision, x, aw.ln_g, aw.ln_b, xn, rows, D, stream);
       if (rc) return rc;
-      rc = mt_pointwise_fwd(precision, xn, aw.w_qkv, nullptr, nullptr, 0, nullptr, 0, qkv, rows, 3 * inner, D, stream);
-      if (rc) return rc;
-      rc = mt_divided_attn_fwd(precision, qkv, mask, identities_mask, mode == 0 ? MT_ATTN_TIME : MT_ATTN_SPACE, o, amap,
-                               batch, f, n, H, cfg->dim_head, ws + l.cls, l.total - l.cls, stream);
-      if (rc) return rc;
+      if (precision == MT_PREC_BF16 && aw.w_qkv_heads && fused_attn_enabled() &&
+          mt_fused_attn_supported(f, n, H, cfg->dim_head, D)) {
+        // projection + attention core in one kernel: qkv stays on chip (attention_fused.cuh)
+        rc = mt_fused_attn_fwd(xn, aw.w_qkv_heads, mask, identities_mask, mode == 0 ? MT_ATTN_TIME : MT_ATTN_SPACE, o, amap,
+                               batch, f, n, H, cfg->dim_head, D, ws + l.cls, l.total - l.cls, stream);
+        if (rc) return rc;
+      } else {
+        rc = mt_pointwise_fwd(precision, xn, aw.w_qkv, nullptr, nullptr, 0, nullptr, 0, qkv, rows, 3 * inner, D, stream);
+        if (rc) return rc;
+        rc = mt_divided_attn_fwd(precision, qkv, mask, identities_mask, mode == 0 ? MT_ATTN_TIME : MT_ATTN_SPACE, o, amap,
+                                 batch, f, n, H, cfg->dim_head, ws + l.cls, l.total - l.cls, stream);
+        if (rc) return rc;
+      }
       rc = mt_linear_residual_fwd(precision, o, aw.w_out, aw.b_out, x, rows, D, inner, stream);
       if (rc) return rc;
     }

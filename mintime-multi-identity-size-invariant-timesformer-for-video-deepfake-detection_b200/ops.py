@@ -102,6 +102,27 @@ def divided_attention(qkv, mask_u8, idmask_u8, mode: str, f: int, n: int, heads:
     return out, cls
 
 
+def fused_attention(xn, w_qkv_heads, mask_u8, idmask_u8, mode: str, f: int, n: int, heads: int, dim_head: int = 64,
+                    want_cls_attn: bool = True):
+    """LayerNorm'd tokens xn (B, 1+f*n, dim) bf16 + per-head weights (heads, 3*dim_head, dim) bf16 ->
+    (out (B,N,heads*dim_head) bf16, cls_attn (B*heads,N) float32): projection + divided attention in one kernel."""
+    _prep(xn, torch.bfloat16)
+    _prep(w_qkv_heads, torch.bfloat16)
+    B, N, dim = xn.shape
+    _lib.require_device(xn.device)
+    out = torch.empty((B, N, heads * dim_head), dtype=torch.bfloat16, device=xn.device)
+    cls = torch.empty((B * heads, N), dtype=torch.float32, device=xn.device) if want_cls_attn else None
+    lib = _lib.load()
+    ws_bytes = int(lib.mt_fused_attn_workspace_bytes(B, f, n, heads))
+    ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=xn.device)
+    with torch.cuda.device(xn.device):
+        rc = lib.mt_fused_attn_fwd(xn.data_ptr(), w_qkv_heads.data_ptr(), mask_u8.data_ptr(), _lib.ptr(idmask_u8),
+                                   _lib.ATTN_TIME if mode == "time" else _lib.ATTN_SPACE, out.data_ptr(), _lib.ptr(cls),
+                                   B, f, n, heads, dim_head, dim, ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+    _lib.check(rc, "mt_fused_attn_fwd")
+    return out, cls
+
+
 def stem(x_nhwc, w27x32, shift, precision="bf16"):
     n, h, w, c = x_nhwc.shape
     assert c == 3

@@ -94,6 +94,14 @@ def geglu_interleave(t: torch.Tensor) -> torch.Tensor:
     return torch.cat([u, g], dim=1).reshape(t.shape)
 
 
+def qkv_per_head(wqkv: torch.Tensor, heads: int, dim_head: int) -> torch.Tensor:
+    """[3*inner][dim] (q rows | k rows | v rows) -> [heads][3*dim_head][dim]: q, k, v rows of head h contiguous -- the
+    operand layout of the fused attention kernel (one 192-row B tile per head)."""
+    inner = heads * dim_head
+    q, k, v = (wqkv[i * inner:(i + 1) * inner].reshape(heads, dim_head, -1) for i in range(3))
+    return torch.cat([q, k, v], dim=1).contiguous()
+
+
 def tsf_cfg_struct(config: dict) -> _lib.TsfCfg:
     m = config["model"]
     c = _lib.TsfCfg()
@@ -129,6 +137,8 @@ def pack_tsf(sd: Dict[str, torch.Tensor], config: dict, precision: str, device) 
             wqkv = sd[p + "fn.to_qkv.weight"].clone()
             wqkv[:inner] *= m["dim-head"] ** -0.5
             a.w_qkv = pk.p(wqkv, T, device)
+            if precision == "bf16":
+                a.w_qkv_heads = pk.p(qkv_per_head(wqkv, m["heads"], m["dim-head"]), T, device)
             a.w_out = pk.p(sd[p + "fn.to_out.0.weight"], T, device)
             a.b_out = pk.p(sd[p + "fn.to_out.0.bias"], f32, device)
         p = f"layers.{l}.2."

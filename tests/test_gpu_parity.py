@@ -149,6 +149,43 @@ def test_divided_attention_core(prec, mode, B, f):
     assert (c[:, :, 1:][dead[:, None, :].expand(B, heads, f * n)] == 0).all()
 
 
+@pytest.mark.parametrize("mode", ["time", "space"])
+@pytest.mark.parametrize("B,f", [(3, 16), (2, 8), (2, 32), (1, 16), (9, 16)])
+def test_fused_attention_matches_unfused_and_oracle(mode, B, f):
+    """mt_fused_attn_fwd (QKV projection + divided attention in one kernel, qkv never in HBM) against (a) the unfused
+    kernels on the same operands and (b) the oracle's Attention.forward (size_invariant_timesformer.py:109-144)."""
+    n, heads, dh, dim = 49, 8, 64, 512
+    N = 1 + f * n
+    g = np.random.default_rng(13 + f)
+    xn = rnd((B, N, dim), 3, 1.0).bfloat16()
+    wqkv = rnd((3 * heads * dh, dim), 5, 0.05)
+    wq_scaled = wqkv.clone()
+    wq_scaled[:heads * dh] *= dh ** -0.5
+    wq_scaled = wq_scaled.bfloat16()
+    mask = torch.from_numpy(g.random((B, f)) > 0.25); mask[:, 0] = True
+    idm = torch.from_numpy(g.random((B, f, f)) > 0.4) | torch.eye(f, dtype=torch.bool)
+    m8, i8 = mask.to(torch.uint8).to(DEV), idm.to(torch.uint8).to(DEV)
+    out, cls = ops.fused_attention(xn.to(DEV), weights.qkv_per_head(wq_scaled, heads, dh).to(DEV), m8, i8, mode, f, n,
+                                   heads, dh)
+    qkv = ops.pointwise(xn.to(DEV).view(B * N, dim), wq_scaled.to(DEV), precision="bf16")
+    out_u, cls_u = ops.divided_attention(qkv.view(B, N, -1), m8, i8, mode, f, n, heads, dh, precision="bf16")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(cls).all()
+    assert rel_err(out.float().cpu(), out_u.float().cpu()) <= 2e-3      # same operands, same attention arithmetic
+    assert rel_err(cls.cpu(), cls_u.cpu()) <= 1e-3
+    # oracle on the bf16-rounded operands: identity out-projection exposes the merged heads
+    sd = {"p.fn.to_qkv.weight": wq_scaled.float(), "p.fn.to_out.0.weight": torch.eye(heads * dh),
+          "p.fn.to_out.0.bias": torch.zeros(heads * dh)}
+    sd["p.fn.to_qkv.weight"][:heads * dh] *= dh ** 0.5                  # the oracle applies the q scale itself
+    ref, ref_cls = orc.divided_attention(xn.float(), sd, "p.", mode, f, n, heads, mask, idm)
+    assert rel_err(out.float().cpu(), ref) <= 8e-3
+    assert rel_err(cls.cpu(), ref_cls.reshape(B * heads, N)) <= 8e-3
+    c = cls.cpu().view(B, heads, N)
+    assert torch.allclose(c.sum(-1), torch.ones(B, heads), atol=1e-5)
+    dead = (~mask).repeat_interleave(n, dim=1)
+    assert (c[:, :, 1:][dead[:, None, :].expand(B, heads, f * n)] == 0).all()
+
+
 def test_head():
     x = rnd((5, 393, 512), 1, 2.0); g = rnd((512,), 2) * 0.1 + 1; b = rnd((512,), 3, 0.1)
     w = rnd((3, 512), 4, 0.05); bias = rnd((3,), 5)
