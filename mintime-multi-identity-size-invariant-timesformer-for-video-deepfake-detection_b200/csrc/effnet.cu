@@ -975,13 +975,32 @@ extern "C" int mt_effnet_b0_fwd(const mt_effnet_b0_weights_t* w, const void* x, 
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   void* cur = ws + l.act_a;
   void* nxt = ws + l.act_b;
+  // Strict algorithmic bytes of SURVEY.md 8(d): every layer's input read once and its output written once, activations
+  // in T, the network input as fp32 -- 4.654 MB per image on the bf16 path (stem 1.405 + 16 MBConv blocks 3.091 + head
+  // 0.157).  Booked on two nested scopes: the whole extractor and the MBConv blocks alone.
+  const double es = precision == MT_PREC_FP32 ? 4.0 : 2.0;
+  double blocks_bytes = 0.0, blocks_flops = 0.0;
+  for (int i = 0; i < 16; ++i) {
+    const BlockSpec& b = kBlocks[i];
+    const double ho = (b.hw + b.s - 1) / b.s, cexp = (double)b.cin * b.e;
+    blocks_bytes += es * ((double)b.hw * b.hw * b.cin + ho * ho * b.cout);
+    blocks_flops += 2.0 * ((b.e != 1 ? (double)b.hw * b.hw * b.cin * cexp : 0.0) + (double)b.k * b.k * ho * ho * cexp +
+                           ho * ho * cexp * b.cout);
+  }
+  const double stem_bytes = 224.0 * 224 * 3 * 4 + es * 112 * 112 * 32, head_bytes = es * 49 * (320 + 1280);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope whole(st, (double)n_img * (blocks_flops + 2.0 * 27 * 32 * 112 * 112 + 2.0 * 49 * 320 * 1280),
+                  (double)n_img * (stem_bytes + blocks_bytes + head_bytes), "extractor (strict bytes)");
   int rc = mt_stem_fwd(precision, x, x_dtype, w->stem_w, w->stem_shift, cur, n_img, 224, 224, stream);
   if (rc) return rc;
-  for (int i = 0; i < 16; ++i) {
-    const mt_mbconv_spec_t b = spec_of(i);
-    rc = mt_mbconv_fwd(precision, &b, &w->blocks[i], cur, nxt, n_img, ws + l.block, l.total - l.block, stream);
-    if (rc) return rc;
-    std::swap(cur, nxt);
+  {
+    ProfScope stack(st, (double)n_img * blocks_flops, (double)n_img * blocks_bytes, "mbconv_stack (strict bytes)");
+    for (int i = 0; i < 16; ++i) {
+      const mt_mbconv_spec_t b = spec_of(i);
+      rc = mt_mbconv_fwd(precision, &b, &w->blocks[i], cur, nxt, n_img, ws + l.block, l.total - l.block, stream);
+      if (rc) return rc;
+      std::swap(cur, nxt);
+    }
   }
   // head 1x1 (320 -> 1280) + BN + swish, written straight into the token layout the patch embedding reads
   return mt_pointwise_fwd(precision, cur, w->head.w, w->head.shift, nullptr, 0, nullptr, 1, feats, n_img * 49, 1280,

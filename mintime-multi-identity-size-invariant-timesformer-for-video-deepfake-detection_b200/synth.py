@@ -36,12 +36,19 @@ def _conv(rng: np.random.Generator, cout: int, cin_per_group: int, k: int, scale
     return torch.from_numpy(w.astype(np.float32))
 
 
-def make_effnet_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]:
+def make_effnet_state_dict(seed: int = 1234, conditioned: bool = False) -> Dict[str, torch.Tensor]:
     """EfficientNet-B0 ``state_dict`` (360 keys, names as in reference model.py:49-87,155-211).
 
     The default ``from_name`` init collapses activations to ~1e-9, which would let any
     kernel pass; this recipe keeps every stage O(1..50): He-normal convs, perturbed BN statistics,
     stem scaled by 1/64 because inputs are raw 0..255 pixels (no normalisation on the path).
+
+    ``conditioned=True`` is the recipe of the bf16 end-to-end fixtures (tests/golden/cond_*.npz): the He-init net above
+    is chaotic -- its residual blocks amplify rounding noise ~30x, the REFERENCE itself moves 0.29-0.42 rel-L2 on the
+    features under bf16 autocast -- so, like a trained network, the residual branches are damped (``_bn2`` gamma of
+    the skip blocks ~ U(0.1, 0.3)), the depthwise filters are scaled by 0.7 and the head conv by 8 to keep the features
+    O(1).  Reference drift under bf16 autocast with these weights: 6e-3 on the features (oracle/measure_ref_bf16_drift.py).
+    Same keys, same shapes, same seeded base values.
     """
     rng = np.random.default_rng(seed)
     sd: Dict[str, torch.Tensor] = {}
@@ -65,6 +72,14 @@ def make_effnet_state_dict(seed: int = 1234) -> Dict[str, torch.Tensor]:
     _bn(rng, HEAD_OUT, "_bn1", sd)
     sd["_fc.weight"] = torch.from_numpy((rng.standard_normal((1000, HEAD_OUT)) * 0.01).astype(np.float32))
     sd["_fc.bias"] = torch.zeros(1000)
+    if conditioned:
+        rng2 = np.random.default_rng(seed + 7)
+        for b in B0_BLOCKS:
+            p = f"_blocks.{b.index}."
+            if b.has_skip:
+                sd[p + "_bn2.weight"] = torch.from_numpy(rng2.uniform(0.1, 0.3, b.cout).astype(np.float32))
+            sd[p + "_depthwise_conv.weight"] = sd[p + "_depthwise_conv.weight"] * 0.7
+        sd["_conv_head.weight"] = sd["_conv_head.weight"] * 8.0
     return sd
 
 

@@ -60,20 +60,60 @@ CASES = {
 }
 
 
-def main():
+# bf16 end-to-end fixtures: the same cases with the CONDITIONED extractor weights (synth.make_effnet_state_dict(...,
+# conditioned=True)), plus 4 clips of the benchmark batch (BASELINE.json configs[1]: B = 32, f = 16, 1 identity,
+# seed 1234 = rank 0 of bench.py) so that bench.py and tests can check the bench-shape run against the reference
+BENCH_CLIPS = [0, 9, 18, 31]
+
+
+def bench_clips():
+    B, f = 32, 16
+    cfg = default_tsf_config(num_frames=f, channels=1280)
+    meta = synth.make_batch_meta(B, f, [1], seed=1234)
+    frames = synth.make_frames(B, f, seed=1234, mask=meta["mask"], dtype=torch.uint8)
+    idx = torch.tensor(BENCH_CLIPS)
+    return cfg, {k: v[idx] for k, v in meta.items()}, frames[idx].float()
+
+
+def main(conditioned: bool = False):
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     EfficientNet, SizeInvariantTimeSformer = load_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
 
-    esd = synth.make_effnet_state_dict(1234)
+    esd = synth.make_effnet_state_dict(1234, conditioned=conditioned)
     ext = EfficientNet.from_name("efficientnet-b0")
     missing = ext.load_state_dict(esd, strict=True)
     ext.eval()
-    print("extractor state_dict keys:", len(esd), missing)
+    print("extractor state_dict keys:", len(esd), missing, "conditioned" if conditioned else "")
+    cases = dict(CASES)
+    if conditioned:
+        cases = {"cond_" + k: v for k, v in CASES.items()}
+        cases["cond_bench_b32_clips"] = None
 
-    for name, (B, f, ids, pad) in CASES.items():
+    for name, spec in cases.items():
+        if spec is None:
+            cfg, meta, frames = bench_clips()
+            B, f = frames.shape[:2]
+            tsd = synth.make_tsf_state_dict(cfg, 4321)
+            model = SizeInvariantTimeSformer(config=cfg, require_attention=True)
+            model.load_state_dict(tsd, strict=True)
+            model.eval()
+            with torch.no_grad():
+                x = frames.permute(0, 1, 4, 2, 3).reshape(B * f, 3, 224, 224)
+                feats = ext(x)
+                logits, (space_attn, time_attn) = model(feats.view(B, f, *feats.shape[1:]), mask=meta["mask"],
+                                                        size_embedding=meta["size_embedding"],
+                                                        identities_mask=meta["identities_mask"], positions=meta["positions"])
+            g = {"clips": np.asarray(BENCH_CLIPS), "tsf.logits": logits.numpy(), "tsf.space_attn": space_attn.numpy(),
+                 "tsf.time_attn": time_attn.numpy(), "ext.head.sample": sample(feats),
+                 "ext.head.absmean": np.float32(feats.abs().mean().item())}
+            path = os.path.join(out_dir, name + ".npz")
+            np.savez_compressed(path, **g)
+            print(name, "logits", logits.flatten().tolist(), "->", path, os.path.getsize(path) // 1024, "KiB")
+            continue
+        B, f, ids, pad = spec
         cfg = default_tsf_config(num_frames=f, channels=1280)
         tsd = synth.make_tsf_state_dict(cfg, 4321)
         model = SizeInvariantTimeSformer(config=cfg, require_attention=True)
@@ -124,4 +164,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--conditioned" in sys.argv:
+        main(conditioned=True)
+    else:
+        main()

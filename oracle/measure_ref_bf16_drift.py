@@ -24,7 +24,7 @@ with warnings.catch_warnings():
     from models.size_invariant_timesformer import SizeInvariantTimeSformer
 
 out = {}
-for name in CASES:
+for name in list(CASES) + ["cond_" + k for k in CASES]:
     cfg, esd, tsd, meta, frames = case_inputs(name)
     g = load_golden(name)
     B, f = frames.shape[:2]

@@ -38,20 +38,35 @@ _CACHE = {}
 
 
 def case_inputs(name):
-    """(cfg, effnet_sd, tsf_sd, meta, frames) for a golden case, rebuilt from the seeds."""
+    """(cfg, effnet_sd, tsf_sd, meta, frames) for a golden case, rebuilt from the seeds.  'cond_<case>' is the same
+    case with the conditioned extractor weights (the bf16 end-to-end fixtures, oracle/make_golden.py --conditioned)."""
     if name in _CACHE:
         return _CACHE[name]
-    B, f, ids, pad = CASES[name]
+    cond = name.startswith("cond_")
+    B, f, ids, pad = CASES[name[5:] if cond else name]
     cfg = default_tsf_config(num_frames=f, channels=1280)
-    if "esd" not in _CACHE:
-        _CACHE["esd"] = synth.make_effnet_state_dict(1234)
+    ekey = "esd_cond" if cond else "esd"
+    if ekey not in _CACHE:
+        _CACHE[ekey] = synth.make_effnet_state_dict(1234, conditioned=cond)
     key = ("tsd", f)
     if key not in _CACHE:
         _CACHE[key] = synth.make_tsf_state_dict(cfg, 4321)
     meta = synth.make_batch_meta(B, f, ids, seed=1234, pad_tail=pad)
     frames = synth.make_frames(B, f, seed=1234, mask=meta["mask"])
-    _CACHE[name] = (cfg, _CACHE["esd"], _CACHE[key], meta, frames)
+    _CACHE[name] = (cfg, _CACHE[ekey], _CACHE[key], meta, frames)
     return _CACHE[name]
+
+
+BENCH_CLIPS = [0, 9, 18, 31]      # oracle/make_golden.py: clips of the bench batch held in cond_bench_b32_clips.npz
+
+
+def bench_batch_inputs():
+    """(cfg, conditioned effnet_sd, tsf_sd, meta, uint8 frames) of bench.py's rank-0 batch (B = 32, f = 16, 1 identity)"""
+    B, f = 32, 16
+    cfg = default_tsf_config(num_frames=f, channels=1280)
+    meta = synth.make_batch_meta(B, f, [1], seed=1234)
+    frames = synth.make_frames(B, f, seed=1234, mask=meta["mask"], dtype=torch.uint8)
+    return cfg, synth.make_effnet_state_dict(1234, conditioned=True), synth.make_tsf_state_dict(cfg, 4321), meta, frames
 
 
 def rel_err(a, b):
