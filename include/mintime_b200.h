@@ -228,12 +228,6 @@ int mt_dwconv_chunks(int precision, int h, int w_, int c, int k, int s);
 int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
                   int n_img, int h, int w_, int c, int k, int s, void* stream);
 
-/* mt_dwconv_fwd + the SE excitation fused in one launch: the last block to finish an image reduces its pool
- * partials and computes gate[i][c] (see mt_se_gate_fwd).  counters: i32 [n_img], zero on entry (left zero). */
-int mt_dwconv_se_fwd(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
-                     int* counters, const float* wr, const float* br, const float* we_t, const float* be, float* gate,
-                     int n_img, int h, int w_, int c, int k, int s, int sq, void* stream);
-
 /* SE excitation (model.py:110-115): mean = sum_chunks(pool_part)/hw;  gate[i][c] = sigmoid(We*swish(Wr*mean + br) + be) */
 int mt_se_gate_fwd(const float* pool_part, int n_chunks, int hw, const float* wr, const float* br, const float* we_t,
                    const float* be, float* gate, int n_img, int c, int sq, void* stream);

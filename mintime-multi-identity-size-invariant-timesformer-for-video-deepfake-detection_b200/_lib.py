@@ -22,7 +22,7 @@ EXPORTS = [
     "mt_pointwise_fwd", "mt_linear_residual_fwd", "mt_linear_geglu_fwd", "mt_patch_embed_fwd",
     "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_fused_attn_supported",
     "mt_fused_attn_workspace_bytes", "mt_fused_attn_fwd", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
-    "mt_dwconv_chunks", "mt_dwconv_se_fwd", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
+    "mt_dwconv_chunks", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
     "mt_aggregate_attn_fwd", "mt_clip_meta_fwd",
     "mt_grad_prep_workspace_bytes", "mt_grad_prep", "mt_linear_wgrad", "mt_colsum_f32", "mt_layernorm_bwd_workspace_bytes", "mt_layernorm_bwd",
     "mt_geglu_fwd", "mt_geglu_bwd", "mt_divided_attn_bwd_workspace_bytes", "mt_divided_attn_bwd", "mt_embed_bwd",
@@ -116,7 +116,6 @@ def load() -> C.CDLL:
     lib.mt_expand_dwconv_chunks.restype = i32
     lib.mt_expand_dwconv_fwd.argtypes = [vp, vp, fp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_dwconv_chunks.argtypes = [i32, i32, i32, i32, i32, i32]
-    lib.mt_dwconv_se_fwd.argtypes = [i32, vp, fp, fp, vp, fp, vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mt_dwconv_chunks.restype = i32
     lib.mt_effnet_b0_block_spec.argtypes = [i32, C.POINTER(MBConvSpec)]
     lib.mt_effnet_b0_block_spec.restype = i32

@@ -270,22 +270,11 @@ inline DwGeom dw_geom(int H, int W, int C, int k, int s) {
   return g;
 }
 
-// Squeeze-excite tail fused into the depthwise kernels: the LAST block to finish an image (per-image
-// arrival counter) reduces that image's pool partials and runs the two tiny FC layers, so the SE gate
-// costs no extra launch and overlaps with the depthwise work of the other images.
-//   wr [SQ][C] (null: no fused SE), br [SQ], we_t [SQ][C], be [C], gate [n_img][C],
-//   counters [n_img] zero on entry / zero again on exit.
-struct SeArgs {
-  const float* wr; const float* br; const float* we_t; const float* be;
-  float* gate; int* counters; int sq; float inv_hw;
-};
-
 template <typename T, int K, int S>
 __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                       const float* __restrict__ shift, T* __restrict__ out,
                                                       float* __restrict__ pool_part, int H, int W, int Ho, int Wo, int C,
-                                                      int pad_lo, int n_oct, int spb, int patches_x, int patches,
-                                                      SeArgs se) {
+                                                      int pad_lo, int n_oct, int spb, int patches_x, int patches) {
   constexpr int SX = dw_sx(S), R = dw_rows(K);
   constexpr int NIN = (SX - 1) * S + K;          // input columns feeding SX outputs
   constexpr int NROW = (R - 1) * S + K;          // input rows feeding R output rows
@@ -382,44 +371,16 @@ __global__ void __launch_bounds__(320) dwconv_kernel(const T* __restrict__ in, c
     for (int sl = 0; sl < spb; ++sl) s += part[(sl * n_oct + o) * 8 + ch];
     pool_part[((size_t)img * gridDim.x + blockIdx.x) * C + c] = s;   // one writer per entry
   }
-  if (se.wr == nullptr) return;
-
-  // ---- fused squeeze-excite (model.py:110-115), executed by the last block of this image
-  __shared__ int is_last;
-  __threadfence();                                 // publish this block's pool partials
-  __syncthreads();
-  if (tid == 0) is_last = atomicAdd(se.counters + img, 1) == (int)gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  if (tid == 0) se.counters[img] = 0;              // leave the counter ready for the next launch
-  float* mean = part;                              // [C]   (dynamic smem is sized for max(blockDim*8, C+SQ))
-  float* sqv = part + C;                           // [SQ]
-  const int n_chunks = gridDim.x;
-  for (int c = tid; c < C; c += blockDim.x) {
-    double acc = 0.0;                              // fixed order, double: deterministic, as accurate as a mean
-    for (int j = 0; j < n_chunks; ++j) acc += (double)__ldcg(pool_part + ((size_t)img * n_chunks + j) * C + c);
-    mean[c] = (float)(acc * (double)se.inv_hw);
-  }
-  __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;   // full warps only (shuffles)
-  for (int j = warp; j < se.sq && warp < nwarps; j += nwarps) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(se.wr[(size_t)j * C + c], mean[c], s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sqv[j] = silu<true>(s + se.br[j]);
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
-    float s = se.be[c];
-    for (int j = 0; j < se.sq; ++j) s = fmaf(se.we_t[(size_t)j * C + c], sqv[j], s);
-    se.gate[(size_t)img * C + c] = sigmoidf_<true>(s);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // SE excitation (model.py:110-115): mean = sum_chunks(pool_part)/hw; gate = sigmoid(We*swish(Wr*mean+br)+be).
+// A separate launch on purpose.  Folding it into the depthwise kernels as a "last block of the image (group) computes the
+// gate" tail was built and measured in round 2: with the kernels' static work striding the block that computes a tail
+// falls behind, so it is the last arriver of its next image as well and ends up computing ALL of its images' gates
+// serially (k5 C1152 H7: 75 -> 1143 us; k3 C32 H112: 192 -> 657 us); and even with dynamic work claims the last groups'
+// tails land after the depthwise work, where one 128..256-thread block needs about as long for the ~10 dependent L2
+// round trips as this 512-thread kernel does including its launch.
 // The arithmetic is tiny (2*SQ*C MACs per image); what costs is streaming the two weight matrices
 // (up to 2 x 48 x 1152 floats) from L2, so one block handles kSeImgs images and every weight it loads feeds
 // kSeImgs FMAs.  `we_t` is the expand weight transposed to [SQ][C] (lanes read consecutive channels).
@@ -565,31 +526,29 @@ int launch_stem_t(const void* x, const float* w, const float* shift, void* out, 
 
 template <typename T, int K, int S>
 int launch_dw_ks(const T* i, const float* w, const float* shift, T* o, float* pool, int n_img, int H, int W, int C,
-                 const SeArgs& se, cudaStream_t st) {
+                 cudaStream_t st) {
   const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
   const DwGeom g = dw_geom(H, W, C, K, S);
   dim3 grid(g.chunks, n_img);
-  const size_t smem = sizeof(float) * (size_t)std::max(g.threads * 8, C + se.sq);
+  const size_t smem = sizeof(float) * (size_t)g.threads * 8;
   dwconv_kernel<T, K, S><<<grid, g.threads, smem, st>>>(i, w, shift, o, pool, H, W, Ho, Wo, C, same_pad_lo(H, K, S),
-                                                        g.n_oct, g.spb, g.patches_x, g.patches, se);
+                                                        g.n_oct, g.spb, g.patches_x, g.patches);
   MT_LAUNCH_CHECK("dwconv_kernel");
   return MT_OK;
 }
 
 template <typename T>
 int launch_dw_t(const void* in, const float* w, const float* shift, void* out, float* pool, int n_img, int H, int W,
-                int C, int k, int s, SeArgs se, cudaStream_t st) {
+                int C, int k, int s, cudaStream_t st) {
   const int Ho = (H + s - 1) / s, Wo = (W + s - 1) / s;
   const T* i = reinterpret_cast<const T*>(in);
   T* o = reinterpret_cast<T*>(out);
-  se.inv_hw = 1.0f / (float)(Ho * Wo);
   ProfScope prof(st, 2.0 * k * k * (double)n_img * Ho * Wo * C,
-                 (double)n_img * C * ((double)H * W + (double)Ho * Wo) * sizeof(T), "dwconv%s k%d s%d C%d H%d",
-                 se.wr ? "+se" : "", k, s, C, H);
-  if (k == 3 && s == 1) return launch_dw_ks<T, 3, 1>(i, w, shift, o, pool, n_img, H, W, C, se, st);
-  if (k == 3 && s == 2) return launch_dw_ks<T, 3, 2>(i, w, shift, o, pool, n_img, H, W, C, se, st);
-  if (k == 5 && s == 1) return launch_dw_ks<T, 5, 1>(i, w, shift, o, pool, n_img, H, W, C, se, st);
-  if (k == 5 && s == 2) return launch_dw_ks<T, 5, 2>(i, w, shift, o, pool, n_img, H, W, C, se, st);
+                 (double)n_img * C * ((double)H * W + (double)Ho * Wo) * sizeof(T), "dwconv k%d s%d C%d H%d", k, s, C, H);
+  if (k == 3 && s == 1) return launch_dw_ks<T, 3, 1>(i, w, shift, o, pool, n_img, H, W, C, st);
+  if (k == 3 && s == 2) return launch_dw_ks<T, 3, 2>(i, w, shift, o, pool, n_img, H, W, C, st);
+  if (k == 5 && s == 1) return launch_dw_ks<T, 5, 1>(i, w, shift, o, pool, n_img, H, W, C, st);
+  if (k == 5 && s == 2) return launch_dw_ks<T, 5, 2>(i, w, shift, o, pool, n_img, H, W, C, st);
   set_error("dwconv: unsupported kernel %d / stride %d", k, s);
   return MT_ERR_UNSUPPORTED;
 }
@@ -644,9 +603,7 @@ int launch_dw_simt(const void* in, const float* w, const float* shift, void* out
   return launch_dw_simt_ks<5, 2>(tm, w, shift, o, pool, n_img, H, C, g, st);
 }
 
-bool dw_simt_ok(int h, int w_, int c, int k, int s, const void* fused_se) {
-  return h == w_ && (k == 3 || k == 5) && (s == 1 || s == 2) && !fused_se;
-}
+bool dw_simt_ok(int h, int w_, int c, int k, int s) { return h == w_ && (k == 3 || k == 5) && (s == 1 || s == 2); }
 
 // ---- fused expand + depthwise (mbconv_fused.cuh).  Measured on B200 at 512 images (us, fused vs expand GEMM +
 // depthwise kernel): block 1 (16->96, 112^2) 503 vs 616; block 2 (24->144, 56^2) 395 vs 383; block 3 328 vs 304;
@@ -725,7 +682,7 @@ int launch_front(const void* in, const void* w_exp, const float* exp_shift, cons
 
 int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
   // tensor-core kernels: a block sees every tile of an image -> one sum per (image, channel)
-  if (precision == MT_PREC_BF16 && dw_simt_ok(h, w_, c, k, s, nullptr)) {
+  if (precision == MT_PREC_BF16 && dw_simt_ok(h, w_, c, k, s)) {
     DwSimtGeom g;
     if (dw_simt_geom(&g, h, w_, c, k, s, 1, 148)) return g.tiles;
   }
@@ -733,18 +690,18 @@ int dw_chunks(int precision, int h, int w_, int c, int k, int s) {
 }
 
 int dwconv_dispatch(int precision, const void* in, const float* w, const float* shift, void* out, float* pool_part,
-                    int n_img, int h, int w_, int c, int k, int s, const SeArgs& se, cudaStream_t st) {
+                    int n_img, int h, int w_, int c, int k, int s, cudaStream_t st) {
   MT_REQUIRE(in && w && shift && out && pool_part, "dwconv: null pointer");
   MT_REQUIRE(n_img > 0 && h > 0 && w_ > 0 && c >= 8 && c % 8 == 0 && c <= 2560,
              "dwconv: bad shape n=%d h=%d w=%d c=%d (c %% 8 == 0)", n_img, h, w_, c);
   MT_REQUIRE(n_img <= 65535, "dwconv: at most 65535 images per call (got %d)", n_img);
-  if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+  if (precision == MT_PREC_FP32) return launch_dw_t<float>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, st);
   if (precision == MT_PREC_BF16) {
-    if (dw_simt_ok(h, w_, c, k, s, se.wr)) return launch_dw_simt(in, w, shift, out, pool_part, n_img, h, c, k, s, st);
-    // non-square maps / fused squeeze-excite tail: register-strip kernel on global loads
-    return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);
+    if (dw_simt_ok(h, w_, c, k, s)) return launch_dw_simt(in, w, shift, out, pool_part, n_img, h, c, k, s, st);
+    // non-square maps: register-strip kernel on global loads
+    return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, st);
   }
-  if (precision == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se, st);  // debug: CUDA-core bf16
+  if (precision == 2) return launch_dw_t<bf16>(in, w, shift, out, pool_part, n_img, h, w_, c, k, s, st);  // debug: CUDA-core bf16
   set_error("dwconv: unknown precision %d", precision);
   return MT_ERR_ARG;
 }
@@ -822,19 +779,7 @@ extern "C" int mt_dwconv_chunks(int precision, int h, int w_, int c, int k, int 
 
 extern "C" int mt_dwconv_fwd(int precision, const void* in, const float* w, const float* shift, void* out,
                              float* pool_part, int n_img, int h, int w_, int c, int k, int s, void* stream) {
-  SeArgs se{};
-  return dwconv_dispatch(precision, in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se,
-                         reinterpret_cast<cudaStream_t>(stream));
-}
-
-extern "C" int mt_dwconv_se_fwd(int precision, const void* in, const float* w, const float* shift, void* out,
-                                float* pool_part, int* counters, const float* wr, const float* br, const float* we_t,
-                                const float* be, float* gate, int n_img, int h, int w_, int c, int k, int s, int sq,
-                                void* stream) {
-  MT_REQUIRE(counters && wr && br && we_t && be && gate && sq > 0, "dwconv_se: null pointer / bad squeeze width");
-  SeArgs se{};
-  se.wr = wr; se.br = br; se.we_t = we_t; se.be = be; se.gate = gate; se.counters = counters; se.sq = sq;
-  return dwconv_dispatch(precision, in, w, shift, out, pool_part, n_img, h, w_, c, k, s, se,
+  return dwconv_dispatch(precision, in, w, shift, out, pool_part, n_img, h, w_, c, k, s,
                          reinterpret_cast<cudaStream_t>(stream));
 }
 

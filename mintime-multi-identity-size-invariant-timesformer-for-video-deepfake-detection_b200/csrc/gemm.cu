@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
   __shared__ float Bs[BK][BN + 4];
   const T* A = reinterpret_cast<const T*>(g.a);
   const T* W = reinterpret_cast<const T*>(g.w);
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;   // (row tiles on x: 512 images x 112^2 pixels exceed grid.y)
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -824,7 +824,7 @@ int launch_tc(const GemmArgs& g, cudaStream_t stream) {
 
 template <typename T, int KIND, bool GATED>
 int launch_simt(const GemmArgs& g, cudaStream_t stream) {
-  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+  dim3 grid((g.M + 63) / 64, (g.N + 63) / 64);
   gemm_simt_kernel<T, KIND, GATED><<<grid, 256, 0, stream>>>(g);
   MT_LAUNCH_CHECK("gemm_simt_kernel");
   return MT_OK;

@@ -177,31 +177,6 @@ def expand_dwconv(x_nhwc, w_exp, exp_shift, w_taps, dw_shift, k: int, s: int):
     return out, pool
 
 
-def dwconv_se(x_nhwc, w_taps, shift, k: int, s: int, wr, br, we_t, be, precision="bf16"):
-    """Depthwise conv + BN + swish with the SE gate computed by the last block of each image.
-    -> (out NHWC, gate (n, c) float32)"""
-    T = _T(precision)
-    _prep(x_nhwc, T)
-    n, h, w, c = x_nhwc.shape
-    sq = wr.shape[0]
-    _lib.require_device(x_nhwc.device)
-    lib = _lib.load()
-    dev = x_nhwc.device
-    out = torch.empty((n, (h + s - 1) // s, (w + s - 1) // s, c), dtype=T, device=dev)
-    pool = torch.empty((n, lib.mt_dwconv_chunks(_lib.prec_id(precision), h, w, c, k, s), c), dtype=torch.float32,
-                       device=dev)
-    counters = torch.zeros((n,), dtype=torch.int32, device=dev)
-    gate = torch.full((n, c), float("nan"), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        rc = lib.mt_dwconv_se_fwd(_lib.prec_id(precision), x_nhwc.data_ptr(), w_taps.data_ptr(), shift.data_ptr(),
-                                  out.data_ptr(), pool.data_ptr(), counters.data_ptr(), wr.data_ptr(), br.data_ptr(),
-                                  we_t.data_ptr(), be.data_ptr(), gate.data_ptr(), n, h, w, c, k, s, sq,
-                                  _lib.stream_ptr())
-    _lib.check(rc, "mt_dwconv_se_fwd")
-    assert int(counters.abs().sum()) == 0, "arrival counters must be left at zero"
-    return out, gate
-
-
 def se_gate(pool_part, hw: int, wr, br, we, be):
     n, chunks, c = pool_part.shape
     sq = wr.shape[0]

@@ -307,24 +307,6 @@ def test_fused_expand_dwconv(k, s, h, cin, cexp):
     assert rel_err(pool.cpu().sum(1), ref.sum((2, 3))) <= 4e-3
 
 
-@pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("k,s,h,c,sq", [(3, 2, 112, 96, 4), (5, 1, 14, 672, 28), (5, 2, 56, 144, 6), (3, 1, 7, 1152, 48)])
-def test_dwconv_with_fused_se_gate(prec, k, s, h, c, sq):
-    """depthwise + SE excitation in one launch (last block per image computes the gate)."""
-    n = 5
-    x = rnd((n, h, h, c), 1).to(T(prec)); w = rnd((c, 1, k, k), 2, 1.0 / k); shift = rnd((c,), 3, 0.3)
-    wr = rnd((sq, c), 4, c ** -0.5); br = rnd((sq,), 5, 0.1); we = rnd((c, sq), 6, sq ** -0.5); be = rnd((c,), 7, 0.1)
-    y = orc.swish(F.conv2d(orc.same_pad(x.float().permute(0, 3, 1, 2), k, s), w, None, s, 0, 1, c) + shift[None, :, None, None])
-    ref_gate = torch.sigmoid(orc.swish(y.mean((2, 3)) @ wr.t() + br) @ we.t() + be)
-    taps = w[:, 0].permute(1, 2, 0).reshape(k * k, c).contiguous()
-    for _ in range(2):      # twice: the arrival counters must come back to zero
-        out, gate = ops.dwconv_se(x.to(DEV), taps.to(DEV), shift.to(DEV), k, s, wr.to(DEV), br.to(DEV),
-                                  we.t().contiguous().to(DEV), be.to(DEV), precision=prec)
-        torch.cuda.synchronize()
-        assert rel_err(out.float().cpu().permute(0, 3, 1, 2), y) <= tol(prec, 1e-5, 4e-3)
-        assert rel_err(gate.cpu(), ref_gate) <= tol(prec, 1e-5, 1e-4)
-
-
 def test_se_gate():
     n, c, sq, hw = 4, 672, 28, 196
     pool = rnd((n, 3, c), 1, 30.0); wr = rnd((sq, c), 2, c ** -0.5); br = rnd((sq,), 3, 0.1)
