@@ -216,6 +216,11 @@ def main():
     ap.add_argument("--attention-maps", action="store_true", help="also return the CLS attention maps (config 5)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE configs[1] (default, the metric's config); train: configs[3], the train.py step")
+    ap.add_argument("--unfrozen", action="store_true",
+                    help="--mode train: the extractor trains too (train.py:155-170: .train(), batch-stat BN, drop-connect, "
+                         "gradients) instead of --freeze_backbone")
+    ap.add_argument("--unfreeze-blocks", type=int, default=-1,
+                    help="--mode train --unfrozen: train only the last k MBConv blocks (train.py --extractor_unfreeze_blocks)")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-path measurement printed beside the bf16 number")
     ap.add_argument("--no-graph", action="store_true",
                     help="call the nn.Modules eagerly instead of replaying the step as a CUDA graph (GraphedHotPath)")

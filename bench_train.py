@@ -122,12 +122,25 @@ def run_train(args, emit, ClockSampler, load_peaks):
     ext = mintime_b200.EfficientNet.from_name("efficientnet-b0", precision=args.precision)
     ext.load_state_dict(synth.make_effnet_state_dict(1234))
     ext = ext.to(dev).eval()                                            # train.py:153-154 (freeze_backbone)
+    unfrozen = bool(getattr(args, "unfrozen", False))
+    if unfrozen:                                                        # train.py:155-170
+        ext.train()
+        k = getattr(args, "unfreeze_blocks", -1)
+        if k >= 0:
+            for name, p in ext.named_parameters():                      # train.py:157-167
+                if name.startswith("_blocks."):
+                    p.requires_grad_(int(name.split(".")[1]) >= 16 - k)
+                else:
+                    p.requires_grad_(name.startswith(("_conv_head", "_bn1")))
+        if world > 1:
+            raise SystemExit("--unfrozen is a single-GPU measurement for now (the extractor's gradients are not bucketed)")
     model = mintime_b200.SizeInvariantTimeSformer(config=cfg, precision=args.precision)
     model.load_state_dict(synth.make_tsf_state_dict(cfg, 4321))
     model = model.to(dev).train()                                       # train.py:315
     if world > 1:
         training.attach_grad_sync(model)
-    opt = torch.optim.SGD(model.parameters(), lr=cfg["training"]["lr"], weight_decay=cfg["training"]["weight-decay"])
+    train_params = list(model.parameters()) + ([p for p in ext.parameters() if p.requires_grad] if unfrozen else [])
+    opt = torch.optim.SGD(train_params, lr=cfg["training"]["lr"], weight_decay=cfg["training"]["weight-decay"])
     lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([0.8169], device=dev))
 
     meta = synth.make_batch_meta(B, f, args.identities, seed=1234 + rank)
@@ -138,8 +151,11 @@ def run_train(args, emit, ClockSampler, load_peaks):
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def train_step(m):
-        with torch.no_grad():                                           # train.py:344-346
+        if unfrozen:                                                    # train.py:347-348
             feats = ext(m["clip"].view(B * f, 224, 224, 3).permute(0, 3, 1, 2)).reshape(B, f, 1280, 7, 7)
+        else:
+            with torch.no_grad():                                       # train.py:344-346
+                feats = ext(m["clip"].view(B * f, 224, 224, 3).permute(0, 3, 1, 2)).reshape(B, f, 1280, 7, 7)
         opt.zero_grad(set_to_none=True)
         y = model(feats, mask=m["mask"], size_embedding=m["size_embedding"], identities_mask=m["identities_mask"],
                   positions=m["positions"])
@@ -163,7 +179,7 @@ def run_train(args, emit, ClockSampler, load_peaks):
     # One process: the whole step (extractor, forward, backward, SGD) replays as ONE CUDA graph
     # (mintime_b200.graphed.GraphedTrainStep); the eager step is bound by its ~900 host-side launches.
     # Data parallel runs stay eager: the per-layer NCCL exchange is issued from inside the backward.
-    use_graph = world == 1 and not args.no_graph
+    use_graph = world == 1 and not args.no_graph and not unfrozen
     graph_kernels = 0
     if use_graph:
         from mintime_b200.graphed import GraphedTrainStep
@@ -208,7 +224,11 @@ def run_train(args, emit, ClockSampler, load_peaks):
     if rank == 0:
         sampler.start()
     # (the first steps of a data-parallel run still set up NCCL channels and grow the side-stream allocator pools)
-    for _ in range(max(args.warmup, 8)):
+    n_warm = 1 if unfrozen else max(args.warmup, 8)
+    if unfrozen:
+        args.steps = min(args.steps, 3)
+        args.warmup = 1
+    for _ in range(n_warm):
         step_resident()
     torch.cuda.synchronize()
     launches0 = lib.mt_prof_launch_count()
@@ -266,10 +286,15 @@ def run_train(args, emit, ClockSampler, load_peaks):
     h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
     emit({
         "metric": "train_videos_per_sec_16f_224px", "value": world * B / (ms * 1e-3), "unit": "videos/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 8), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[3]: train.py step, frozen EfficientNet-B0 (eval, no_grad) -> "
-                               "SizeInvariantTimeSformer forward + backward + SGD, synthetic ForgeryNet-shaped clips",
+        "config": {"workload": ("BASELINE.json configs[3]: train.py step, TRAINABLE EfficientNet-B0 (.train(): batch-stat BN, "
+                                "drop-connect, fp32 forward + backward, csrc/effnet_train.cu"
+                                + (f", last {args.unfreeze_blocks} blocks unfrozen" if getattr(args, "unfreeze_blocks", -1) >= 0 else "")
+                                + ") -> SizeInvariantTimeSformer forward + backward + SGD over both modules"
+                                if unfrozen else
+                                "BASELINE.json configs[3]: train.py step, frozen EfficientNet-B0 (eval, no_grad) -> "
+                                "SizeInvariantTimeSformer forward + backward + SGD") + ", synthetic ForgeryNet-shaped clips",
                    "batch_per_gpu": B, "frames": f, "identities": ",".join(map(str, args.identities)),
                    "precision": args.precision + " compute, fp32 master weights and gradients",
                    "launch": "one CUDA-graph replay per step (GraphedTrainStep)" if use_graph else "eager nn.Module / autograd calls",

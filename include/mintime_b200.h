@@ -214,6 +214,53 @@ int mt_fused_attn_fwd(const void* xn, const void* w_qkv_heads, const uint8_t* ma
                       int mode, void* out, float* cls_attn, int batch, int f, int n, int heads, int dim_head, int dim,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * EfficientNet-B0 in TRAIN mode (train.py:153-170: the extractor trains unless --freeze_backbone): fp32 NHWC building
+ * blocks of MBConvBlock.forward / backward (model.py:89-128) that the eval path folds away.  1x1 convolutions use
+ * mt_pointwise_fwd (forward; data gradient on the transposed weight) and mt_grad_prep + mt_linear_wgrad.
+ * Orchestrated by mintime_b200/efficientnet_train.py.  `workspace`: mt_extractor_train_workspace_bytes(rows, c).
+ * ------------------------------------------------------------------------------------------- */
+size_t mt_extractor_train_workspace_bytes(long long rows, int c);
+/* nn.BatchNorm2d in train mode (utils.py:520-521): per-channel mean / BIASED variance of x [rows][c]; when running_* are
+ * given they move by `momentum` towards mean / UNBIASED variance (in place). */
+int mt_bn_stats(const float* x, float* mean, float* var, float* running_mean, float* running_var, float momentum,
+                long long rows, int c, void* workspace, size_t workspace_bytes, void* stream);
+/* out = act(gamma * (x - mean) / sqrt(var + eps) + beta), act 0 = none, 1 = swish (utils.py:64-69) */
+int mt_bn_act_fwd(const float* x, const float* mean, const float* var, const float* gamma, const float* beta, int act,
+                  float eps, float* out, long long rows, int c, void* stream);
+/* backward of mt_bn_act_fwd through the batch statistics (swish backward utils.py:71-80): dx, dgamma [c], dbeta [c] */
+int mt_bn_act_bwd(const float* dy, const float* x, const float* mean, const float* var, const float* gamma,
+                  const float* beta, int act, float eps, float* dx, float* dgamma, float* dbeta, long long rows, int c,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* raw stem conv 3x3 s2 3->32, TF-SAME padding (utils.py:248-276): x [n][h][w][3], w [27][32] tap-major -> out [n][h/2][w/2][32];
+ * mt_stem_wgrad: dw [27][32] = the weight gradient for output gradient dy */
+int mt_stem_raw_fwd(const float* x, const float* w, float* out, int n_img, int h, int w_, void* stream);
+int mt_stem_wgrad(const float* x, const float* dy, float* dw, int n_img, int h, int w_, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* raw depthwise kxk stride s, TF-SAME padding: in [n][h][h][c], w [k*k][c] tap-major -> out [n][ho][ho][c]; data / weight gradients */
+int mt_dwconv_raw_fwd(const float* in, const float* w, float* out, int n_img, int h, int c, int k, int s, void* stream);
+int mt_dwconv_dgrad(const float* dy, const float* w, float* dx, int n_img, int h, int c, int k, int s, void* stream);
+int mt_dwconv_wgrad(const float* in, const float* dy, float* dw, int n_img, int h, int c, int k, int s, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* weight gradient of a 1x1 convolution: dw [co][ci] = dy [rows][co]^T a [rows][ci] (any channel counts; fixed-order sums) */
+size_t mt_conv1x1_wgrad_workspace_bytes(long long rows, int co, int ci);
+int mt_conv1x1_wgrad(const float* dy, const float* a, float* dw, long long rows, int co, int ci, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* squeeze-excite (model.py:110-115): pooled mean of x [groups][rows][c]; the two FC layers (wr [sq][c], we [c][sq], the
+ * reference's layouts) -> gate [n][c] (+ s_pre [n][sq] kept for the backward); their backward; the gate multiply's. */
+int mt_group_mean(const float* x, float* out, int groups, int rows, int c, void* stream);
+int mt_se_fc_fwd(const float* mean, const float* wr, const float* br, const float* we, const float* be, float* gate,
+                 float* s_pre, int n_img, int c, int sq, void* stream);
+int mt_se_fc_bwd(const float* dgate, const float* gate, const float* s_pre, const float* mean, const float* wr,
+                 const float* we, float* dmean, float* dwr, float* dbr, float* dwe, float* dbe, int n_img, int c, int sq,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int mt_gate_mul(const float* x, const float* gate, float* out, int n_img, int rows, int c, void* stream);
+/* phase 0: dgate [n][c] = sum_rows dxg * x;  phase 1: dx = dxg * gate + dmean / rows (gate multiply + avg-pool backward) */
+int mt_gate_bwd(const float* dxg, const float* x, const float* gate, const float* dmean, float* dgate, float* dx, int n_img,
+                int rows, int c, int phase, void* stream);
+/* out = x * scale[image] (+ skip): drop-connect (utils.py:129-154) + residual add (model.py:123-127); scale / skip may be NULL */
+int mt_scale_add(const float* x, const float* scale, const float* skip, float* out, int n_img, long long per_img, void* stream);
+
 /* Stem: ZeroPad2d(0,1,0,1) + conv 3x3 s2 (3->32) + BN + swish (utils.py:248-276, model.py:276)
  *   x NHWC [n_img][H][W][3] (f32/u8) -> out T NHWC [n_img][H/2][W/2][32] */
 int mt_stem_fwd(int precision, const void* x, int x_dtype, const float* w, const float* shift, void* out, int n_img,

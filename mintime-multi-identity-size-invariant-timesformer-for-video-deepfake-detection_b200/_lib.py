@@ -26,7 +26,10 @@ EXPORTS = [
     "mt_aggregate_attn_fwd", "mt_clip_meta_fwd",
     "mt_grad_prep_workspace_bytes", "mt_grad_prep", "mt_linear_wgrad", "mt_colsum_f32", "mt_layernorm_bwd_workspace_bytes", "mt_layernorm_bwd",
     "mt_geglu_fwd", "mt_geglu_bwd", "mt_divided_attn_bwd_workspace_bytes", "mt_divided_attn_bwd", "mt_embed_bwd",
-    "mt_head_bwd_workspace_bytes", "mt_head_bwd", "mt_prof_enable", "mt_prof_reset", "mt_prof_collect", "mt_prof_launch_count",
+    "mt_head_bwd_workspace_bytes", "mt_head_bwd",
+    "mt_extractor_train_workspace_bytes", "mt_bn_stats", "mt_bn_act_fwd", "mt_bn_act_bwd", "mt_stem_raw_fwd", "mt_stem_wgrad",
+    "mt_dwconv_raw_fwd", "mt_dwconv_dgrad", "mt_dwconv_wgrad", "mt_group_mean", "mt_se_fc_fwd", "mt_se_fc_bwd", "mt_gate_mul",
+    "mt_gate_bwd", "mt_scale_add", "mt_conv1x1_wgrad_workspace_bytes", "mt_conv1x1_wgrad", "mt_prof_enable", "mt_prof_reset", "mt_prof_collect", "mt_prof_launch_count",
 ]
 
 vp, fp, i32, sz = C.c_void_p, C.c_void_p, C.c_int, C.c_size_t   # all device pointers travel as void*
@@ -142,6 +145,26 @@ def load() -> C.CDLL:
     lib.mt_head_bwd_workspace_bytes.argtypes = [i32, i32, i32]
     lib.mt_head_bwd_workspace_bytes.restype = sz
     lib.mt_head_bwd.argtypes = [fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, vp, sz, vp]
+    i64, f32 = C.c_longlong, C.c_float
+    lib.mt_extractor_train_workspace_bytes.argtypes = [i64, i32]
+    lib.mt_extractor_train_workspace_bytes.restype = sz
+    lib.mt_bn_stats.argtypes = [fp, fp, fp, fp, fp, f32, i64, i32, vp, sz, vp]
+    lib.mt_bn_act_fwd.argtypes = [fp, fp, fp, fp, fp, i32, f32, fp, i64, i32, vp]
+    lib.mt_bn_act_bwd.argtypes = [fp, fp, fp, fp, fp, fp, i32, f32, fp, fp, fp, i64, i32, vp, sz, vp]
+    lib.mt_stem_raw_fwd.argtypes = [fp, fp, fp, i32, i32, i32, vp]
+    lib.mt_stem_wgrad.argtypes = [fp, fp, fp, i32, i32, i32, vp, sz, vp]
+    lib.mt_dwconv_raw_fwd.argtypes = [fp, fp, fp, i32, i32, i32, i32, i32, vp]
+    lib.mt_dwconv_dgrad.argtypes = [fp, fp, fp, i32, i32, i32, i32, i32, vp]
+    lib.mt_dwconv_wgrad.argtypes = [fp, fp, fp, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.mt_conv1x1_wgrad_workspace_bytes.argtypes = [i64, i32, i32]
+    lib.mt_conv1x1_wgrad_workspace_bytes.restype = sz
+    lib.mt_conv1x1_wgrad.argtypes = [fp, fp, fp, i64, i32, i32, vp, sz, vp]
+    lib.mt_group_mean.argtypes = [fp, fp, i32, i32, i32, vp]
+    lib.mt_se_fc_fwd.argtypes = [fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, vp]
+    lib.mt_se_fc_bwd.argtypes = [fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, vp, sz, vp]
+    lib.mt_gate_mul.argtypes = [fp, fp, fp, i32, i32, i32, vp]
+    lib.mt_gate_bwd.argtypes = [fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, vp]
+    lib.mt_scale_add.argtypes = [fp, fp, fp, fp, i32, i64, vp]
     lib.mt_prof_enable.argtypes = [i32]
     lib.mt_prof_enable.restype = None
     lib.mt_prof_reset.restype = None
@@ -150,7 +173,9 @@ def load() -> C.CDLL:
     lib.mt_prof_launch_count.restype = C.c_ulonglong
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name.endswith(("_fwd", "_bwd")) or name in ("mt_grad_prep", "mt_colsum_f32", "mt_linear_wgrad"):
+        if name.endswith(("_fwd", "_bwd")) or name in ("mt_grad_prep", "mt_colsum_f32", "mt_linear_wgrad", "mt_bn_stats",
+                                                       "mt_stem_wgrad", "mt_dwconv_dgrad", "mt_dwconv_wgrad", "mt_group_mean",
+                                                       "mt_gate_mul", "mt_scale_add", "mt_conv1x1_wgrad"):
             fn.restype = i32
     if lib.mt_abi_version() != 4:
         raise RuntimeError("mintime_b200: ABI version mismatch between _lib.py and libmintime_b200.so")

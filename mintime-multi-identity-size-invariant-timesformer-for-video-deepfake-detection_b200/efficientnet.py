@@ -10,7 +10,8 @@ libmintime_b200.so (mt_effnet_b0_fwd).  There is no PyTorch fallback.
 Differences a caller can see (documented in INTEGRATION.md):
   * output is NHWC memory viewed as (n,1280,7,7) (what ``rearrange('b f c h w -> b (f h w) c')`` wants),
     dtype float32 for precision='fp32', bfloat16 for precision='bf16' (default);
-  * only eval-mode forward exists in this round: calling forward in train mode raises.
+  * train mode (``.train()``, train.py:153-170) runs batch-statistics BatchNorm + drop-connect and is differentiable
+    (efficientnet_train.py); it computes in float32 whatever ``precision`` says and returns float32 features.
 """
 from __future__ import annotations
 
@@ -57,6 +58,8 @@ class EfficientNet(nn.Module):
         self._conv_head = nn.Conv2d(B0_BLOCKS[-1].cout, HEAD_OUT, 1, bias=False)
         self._bn1 = nn.BatchNorm2d(HEAD_OUT, momentum=BN_MOMENTUM, eps=BN_EPS)
         self._fc = nn.Linear(HEAD_OUT, 1000)          # present in reference checkpoints; unused by forward
+        self.drop_connect_rate = 0.2                  # GlobalParams.drop_connect_rate of efficientnet-b0 (utils.py:523)
+        self._drop_connect_rand = None                # test hook: callable(n) -> n uniform draws (default: torch.rand on the device)
         self._packed: Optional[weights.Packed] = None
         self._packed_key = None
         self._ws = None
@@ -72,9 +75,13 @@ class EfficientNet(nn.Module):
         if in_channels != 3:
             raise ValueError("the MINTIME path feeds 3-channel face crops (in_channels=3)")
         precision = override_params.pop("precision", "bf16")
+        drop = override_params.pop("drop_connect_rate", None)
         if override_params.get("image_size", 224) != 224:
             raise ValueError("the B200 extractor is built for 224x224 crops (config image-size: 224)")
-        return cls(model_name, precision=precision)
+        model = cls(model_name, precision=precision)
+        if drop is not None:
+            model.drop_connect_rate = float(drop)
+        return model
 
     @classmethod
     def from_pretrained(cls, model_name, weights_path=None, advprop=False, in_channels=3, num_classes=1000,
@@ -132,10 +139,6 @@ class EfficientNet(nn.Module):
         """inputs: (n,3,224,224) float32 / uint8 -- ideally the permuted NHWC view the callers build
         (train.py:341 ``rearrange(videos, 'b f h w c -> (b f) c h w')``), raw 0..255.
         Returns (n,1280,7,7) (NHWC memory)."""
-        if self.training:
-            raise NotImplementedError(
-                "mintime_b200.EfficientNet: train-mode forward (batch-stat BN + drop-connect, model.py:125-127) is "
-                "not built yet; call .eval() (the reference's --freeze_backbone mode)")
         if inputs.dim() != 4 or inputs.shape[1:] != (3, 224, 224):
             raise ValueError(f"expected (n,3,224,224), got {tuple(inputs.shape)}")
         _lib.require_device(inputs.device)
@@ -146,6 +149,13 @@ class EfficientNet(nn.Module):
         x = inputs.permute(0, 2, 3, 1)
         if not x.is_contiguous():
             x = x.contiguous()          # plumbing: caller gave true NCHW memory
+        if self.training:
+            # train.py:153-170: batch-statistics BatchNorm (+ running-stat update), drop-connect, gradients for the
+            # parameters that require them -- fp32 kernels of csrc/effnet_train.cu, returns float32 features
+            from . import efficientnet_train
+            feats = efficientnet_train.forward_train(self, x.float() if x.dtype != torch.float32 else x,
+                                                     self._drop_connect_rand)
+            return feats.permute(0, 3, 1, 2)
         T = _lib.torch_dtype(self.precision)
         prec = _lib.prec_id(self.precision)
         with torch.cuda.device(inputs.device):

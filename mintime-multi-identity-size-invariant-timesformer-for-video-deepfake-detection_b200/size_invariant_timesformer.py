@@ -212,9 +212,6 @@ class SizeInvariantTimeSformer(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training step (train.py:355, 376-378): forward that keeps activations + hand-written backward
             from . import training
-            if x.requires_grad:
-                raise NotImplementedError("gradients w.r.t. the input features (an unfrozen extractor, train.py:155-170) "
-                                          "are not produced; run the extractor under no_grad (--freeze_backbone)")
             out = training.TsfTrainFunction.apply(self, tok.reshape(b, f * n, c), mask_u8, idm_u8, se, pos,
                                                   *self.parameters())
             if self.require_attention:

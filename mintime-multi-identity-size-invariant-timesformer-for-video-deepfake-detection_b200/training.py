@@ -1,8 +1,8 @@
 """Training path of ``SizeInvariantTimeSformer``: what ``loss.backward()`` runs in the reference's train.py:376-378.
 
-Scope: the transformer trains, the feature extractor is frozen (``--freeze_backbone``: train.py:153-154, 344-346 -- the
-extractor runs in eval mode under ``no_grad``); gradients w.r.t. the input features are not produced (asking for them
-raises).  The forward is the schedule of size_invariant_timesformer.py:224-276 with the activations the backward needs
+Scope: the transformer's forward / backward.  With a frozen extractor (``--freeze_backbone``: train.py:153-154, 344-346)
+the features arrive without a graph; with a trainable one (train.py:155-170, efficientnet_train.py) the backward also
+returns d loss / d features (the patch embedding's data gradient) and autograd carries it into the extractor.  The forward is the schedule of size_invariant_timesformer.py:224-276 with the activations the backward needs
 kept; the backward is hand-scheduled over the kernels of csrc/train.cu and the forward GEMMs (dgrad / wgrad as GEMMs on
 transposed operands).  It is exposed as ONE ``torch.autograd.Function`` so that the reference's training loop
 (``optimizer.zero_grad(); loss.backward(); optimizer.step()``) works unchanged: the gradients land in ``param.grad``
@@ -49,7 +49,9 @@ class TrainPack:
             self.keep.append(t)
             return t
 
-        W.w_patch = dev(sd["to_patch_embedding.weight"], T).data_ptr()
+        self.w_patch = dev(sd["to_patch_embedding.weight"], T)
+        self.w_patch_t = dev(self.w_patch.t(), T)          # [C][dim]: data gradient w.r.t. the extractor's features
+        W.w_patch = self.w_patch.data_ptr()
         W.b_patch = dev(sd["to_patch_embedding.bias"], f32).data_ptr()
         W.cls_token = dev(sd["cls_token"].reshape(-1), f32).data_ptr()
         W.pos_emb = dev(sd["pos_emb.weight"], f32).data_ptr()
@@ -312,7 +314,9 @@ class TsfTrainFunction(torch.autograd.Function):
         # (size_invariant_timesformer.py:237-238); `pos` is None then and the kernel scatters to rows 0..N-1
         dpos, dsize, dcls = ops.embed_bwd(g3, pos, se, rows, f, n, want_pos=True, want_size=bool(model.enable_size_emb))
         Mt = B * f * n
-        _, _, cs = ops.grad_prep(g, want_colsum=True, rows_per_batch=f * n, m=Mt, precision=precision)
+        want_dtok = ctx.needs_input_grad[1]            # an unfrozen extractor (train.py:155-170) wants d loss / d features
+        gtok, _, cs = ops.grad_prep(g, want_rm=want_dtok, want_colsum=True, rows_per_batch=f * n, m=Mt, precision=precision)
+        dtok = ops.pointwise(gtok, pk.w_patch_t, precision=precision).view(B, f * n, -1) if want_dtok else None
         dwp = torch.zeros((dim, model.channels), dtype=f32, device=dev)
         wgrad(dwp, g, tok.view(Mt, -1), rows_per_batch=f * n, m=Mt)     # (g is final here: nothing writes it any more)
         for s_ in side:
@@ -334,6 +338,7 @@ class TsfTrainFunction(torch.autograd.Function):
             sync.finish()
         ctx.saved = None
         out = [None] * ctx.n_extra
+        out[1] = dtok
         for name, p in zip(ctx.param_names, model.parameters()):
             gr = grads.get(name)
             out.append(gr.view_as(p) if (gr is not None and p.requires_grad) else None)

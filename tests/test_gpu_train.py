@@ -6,6 +6,7 @@ import copy
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import mintime_b200  # noqa: F401
 from mintime_b200 import SizeInvariantTimeSformer, ops, weights
@@ -323,10 +324,6 @@ def test_eval_after_train_uses_updated_weights_and_frozen_params_get_no_grad():
         e1 = model(x, mask=meta["mask"].to(DEV), size_embedding=meta["size_embedding"],
                    identities_mask=meta["identities_mask"].to(DEV), positions=meta["positions"].to(DEV))
     assert (e1 - e0).abs().max() > 1e-3                      # the packed copies were rebuilt from the new parameters
-    with pytest.raises(NotImplementedError):
-        model(x.clone().float().requires_grad_(True).bfloat16(), mask=meta["mask"].to(DEV),
-              size_embedding=meta["size_embedding"], identities_mask=meta["identities_mask"].to(DEV),
-              positions=meta["positions"].to(DEV))
 
 
 def test_graphed_train_step_matches_eager_steps():
@@ -398,3 +395,198 @@ def test_training_forward_returns_attention_maps_too():
     assert (y2 - y.detach()).abs().max() <= 2e-2
     assert rel_err(sa, sa2) <= 1e-2 and rel_err(ta, ta2) <= 1e-2
     assert torch.allclose(sa.sum(-1), torch.ones_like(sa.sum(-1)), atol=1e-3)
+
+
+# --------------------------------------------------------------------------------------------- extractor in train mode
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("rows,c", [(4 * 49, 1152), (3 * 56 * 56, 24), (1000, 33)])
+def test_batchnorm_train_fwd_bwd(act, rows, c):
+    """mt_bn_stats / mt_bn_act_fwd / mt_bn_act_bwd against F.batch_norm(training=True) (+ swish) under autograd, and the
+    running-statistics update of nn.BatchNorm2d (momentum 0.01, unbiased variance)."""
+    from mintime_b200 import efficientnet_train as et
+    g = torch.Generator().manual_seed(rows + c)
+    x = (torch.randn((rows, c), generator=g) * 2 + 0.5)
+    gamma = torch.rand((c,), generator=g) + 0.5; beta = torch.randn((c,), generator=g) * 0.1
+    dy = torch.randn((rows, c), generator=g)
+    bn = torch.nn.BatchNorm2d(c, momentum=0.01, eps=1e-3)
+    bn.running_mean.copy_(torch.randn((c,), generator=g) * 0.1); bn.running_var.copy_(torch.rand((c,), generator=g) + 0.5)
+    bn.weight.data.copy_(gamma); bn.bias.data.copy_(beta)
+    ref_bn = copy.deepcopy(bn).double().train()
+    xr = x.double().clone().requires_grad_(True)
+    z = ref_bn(xr.t().reshape(1, c, rows, 1))
+    yr = (z * torch.sigmoid(z)) if act else z
+    yr.backward(dy.double().t().reshape(1, c, rows, 1))
+    bn = bn.to(DEV)
+    ws = et._Ws()
+    xd = x.to(DEV)
+    mean, var = et.bn_train(xd, bn, ws)
+    y = et.bn_act(xd, mean, var, bn.weight.detach(), bn.bias.detach(), act)
+    dx, dg, db = et.bn_act_bwd(dy.to(DEV), xd, mean, var, bn.weight.detach(), bn.bias.detach(), act, ws)
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), yr.detach().reshape(c, rows).t()) <= 1e-5
+    assert rel_err(dx.cpu(), xr.grad) <= 2e-5
+    assert rel_err(dg.cpu(), ref_bn.weight.grad) <= 2e-5 and rel_err(db.cpu(), ref_bn.bias.grad) <= 2e-5
+    assert torch.allclose(bn.running_mean.cpu().double(), ref_bn.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bn.running_var.cpu().double(), ref_bn.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("k,s,h,c", [(3, 1, 14, 40), (3, 2, 28, 24), (5, 1, 7, 48), (5, 2, 14, 33), (5, 2, 9, 8)])
+def test_depthwise_raw_fwd_dgrad_wgrad(k, s, h, c):
+    """raw depthwise conv with TF-SAME padding (utils.py:248-276) and both gradients, against autograd in fp64"""
+    from mintime_b200 import _lib, efficientnet_train as et
+    n = 3
+    g = torch.Generator().manual_seed(k * 100 + h)
+    x = torch.randn((n, c, h, h), generator=g); w = torch.randn((c, 1, k, k), generator=g) / k
+    ho = (h + s - 1) // s
+    dy = torch.randn((n, c, ho, ho), generator=g)
+    xr, wr_ = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = F.conv2d(orc.same_pad(xr, k, s), wr_, None, s, 0, 1, c)
+    yr.backward(dy.double())
+    lib = _lib.load()
+    xd, dyd, taps = _nhwc(x).to(DEV), _nhwc(dy).to(DEV), et._taps(w).to(DEV)
+    out = torch.empty((n, ho, ho, c), device=DEV); dx = torch.empty((n, h, h, c), device=DEV)
+    dw = torch.empty((k * k, c), device=DEV)
+    ws = et._Ws().get(n * ho * ho, c, torch.device(DEV))
+    st = _lib.stream_ptr()
+    _lib.check(lib.mt_dwconv_raw_fwd(xd.data_ptr(), taps.data_ptr(), out.data_ptr(), n, h, c, k, s, st))
+    _lib.check(lib.mt_dwconv_dgrad(dyd.data_ptr(), taps.data_ptr(), dx.data_ptr(), n, h, c, k, s, st))
+    _lib.check(lib.mt_dwconv_wgrad(xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), n, h, c, k, s, ws.data_ptr(), ws.numel(), st))
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().permute(0, 3, 1, 2), yr.detach()) <= 1e-5
+    assert rel_err(dx.cpu().permute(0, 3, 1, 2), xr.grad) <= 1e-5
+    assert rel_err(et._untaps(dw, k).cpu(), wr_.grad) <= 1e-5
+
+
+def test_squeeze_excite_fwd_bwd():
+    """pooled mean -> the two SE FC layers -> gate multiply (model.py:110-115), forward and all gradients vs autograd"""
+    from mintime_b200 import _lib, efficientnet_train as et
+    n, hw, c, sq = 5, 49, 96, 4
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((n, hw, c), generator=g)
+    wr = torch.randn((sq, c), generator=g) * c ** -0.5; br = torch.randn((sq,), generator=g) * 0.1
+    we = torch.randn((c, sq), generator=g) * sq ** -0.5; be = torch.randn((c,), generator=g) * 0.1
+    dout = torch.randn((n, hw, c), generator=g)
+    leaves = [t.double().requires_grad_(True) for t in (x, wr, br, we, be)]
+    xr, wrr, brr, wer, ber = leaves
+    pm = xr.mean(1)
+    sp = pm @ wrr.t() + brr
+    gate = torch.sigmoid((sp * torch.sigmoid(sp)) @ wer.t() + ber)
+    (xr * gate[:, None, :]).backward(dout.double())
+    lib, st = _lib.load(), _lib.stream_ptr()
+    D = lambda t: t.to(DEV).contiguous()
+    xd, dd = D(x), D(dout)
+    pmd = torch.empty((n, c), device=DEV); gated = torch.empty((n, c), device=DEV); spd = torch.empty((n, sq), device=DEV)
+    _lib.check(lib.mt_group_mean(xd.data_ptr(), pmd.data_ptr(), n, hw, c, st))
+    wrd, brd, wed, bed = D(wr), D(br), D(we), D(be)
+    _lib.check(lib.mt_se_fc_fwd(pmd.data_ptr(), wrd.data_ptr(), brd.data_ptr(), wed.data_ptr(), bed.data_ptr(), gated.data_ptr(),
+                                spd.data_ptr(), n, c, sq, st))
+    # out = x * gate: d(out)/dx needs dgate first
+    dgate = torch.empty((n, c), device=DEV)
+    _lib.check(lib.mt_gate_bwd(dd.data_ptr(), xd.data_ptr(), None, None, dgate.data_ptr(), None, n, hw, c, 0, st))
+    dpm = torch.empty((n, c), device=DEV); dwr = torch.empty((sq, c), device=DEV); dbr = torch.empty((sq,), device=DEV)
+    dwe = torch.empty((c, sq), device=DEV); dbe = torch.empty((c,), device=DEV)
+    ws = et._Ws().get(n * hw, c, torch.device(DEV))
+    _lib.check(lib.mt_se_fc_bwd(dgate.data_ptr(), gated.data_ptr(), spd.data_ptr(), pmd.data_ptr(), wrd.data_ptr(), wed.data_ptr(),
+                                dpm.data_ptr(), dwr.data_ptr(), dbr.data_ptr(), dwe.data_ptr(), dbe.data_ptr(), n, c, sq,
+                                ws.data_ptr(), ws.numel(), st))
+    dx = torch.empty_like(xd)
+    _lib.check(lib.mt_gate_bwd(dd.data_ptr(), None, gated.data_ptr(), dpm.data_ptr(), None, dx.data_ptr(), n, hw, c, 1, st))
+    torch.cuda.synchronize()
+    assert rel_err(gated.cpu(), gate.detach()) <= 1e-5
+    for got, ref, name in ((dx, xr.grad, "dx"), (dwr, wrr.grad, "dwr"), (dbr, brr.grad, "dbr"), (dwe, wer.grad, "dwe"),
+                           (dbe, ber.grad, "dbe")):
+        assert rel_err(got.cpu(), ref) <= 2e-5, name
+
+
+@pytest.mark.parametrize("tag,rate", [("nodrop", 0.0), ("drop", 0.2)])
+def test_extractor_train_mode_matches_reference(tag, rate):
+    """EfficientNet in .train() (train.py:153-170): batch-statistics BatchNorm + running-stat update, drop-connect,
+    loss.backward() through csrc/effnet_train.cu -- against the UNMODIFIED reference in .train() on the same 4 faces
+    (tests/golden/extractor_train.npz): outputs 2e-4, gradients 2e-3, running statistics 1e-4.  The drop-connect draws come
+    from the CPU generator here because the fixture was produced on the CPU (the default is the device's, like the reference)."""
+    from helpers import EXTRACTOR_TRAIN_KEYS, extractor_train_inputs
+    from mintime_b200 import EfficientNet
+    gold = load_golden("extractor_train")
+    esd, x, probe = extractor_train_inputs()
+    ext = EfficientNet.from_name("efficientnet-b0", precision="fp32", drop_connect_rate=rate)
+    ext.load_state_dict(esd)
+    ext = ext.to(DEV).train()
+    ext._drop_connect_rand = lambda n: torch.rand([n, 1, 1, 1])           # CPU generator, reference call (utils.py:146)
+    torch.manual_seed(7)
+    out = ext(x.to(DEV))                                                   # (4,1280,7,7) view of NHWC memory
+    assert out.shape == (4, 1280, 7, 7) and out.dtype == torch.float32 and out.requires_grad
+    (out * probe.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    scale = float(gold[f"{tag}.out_absmean"])
+    assert np.abs(sample(out.contiguous()) - gold[f"{tag}.out"]).max() <= 2e-4 * max(scale, 1.0)
+    params = dict(ext.named_parameters())
+    for k in EXTRACTOR_TRAIN_KEYS:
+        ref = gold[f"{tag}.grad.{k}"]
+        got = sample(params[k].grad, 512)
+        assert np.linalg.norm(got - ref) <= 2e-3 * np.linalg.norm(ref) + 1e-8, (k, np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        assert abs(float(params[k].grad.double().norm()) - float(gold[f"{tag}.gradnorm.{k}"])) <= 2e-3 * float(gold[f"{tag}.gradnorm.{k}"])
+    bufs = dict(ext.named_buffers())
+    for k in ("_bn0", "_blocks.0._bn1", "_blocks.5._bn0", "_blocks.15._bn2", "_bn1"):
+        assert np.allclose(bufs[k + ".running_mean"].cpu().numpy(), gold[f"{tag}.{k}.running_mean"], rtol=1e-4, atol=1e-5), k
+        assert np.allclose(bufs[k + ".running_var"].cpu().numpy(), gold[f"{tag}.{k}.running_var"], rtol=1e-4, atol=1e-5), k
+        assert int(bufs[k + ".num_batches_tracked"]) == 1
+    assert all(p.grad is not None for n_, p in params.items() if not n_.startswith("_fc"))
+
+
+def test_extractor_partial_unfreeze_and_eval_after_train():
+    """--extractor_unfreeze_blocks k (train.py:157-167): only the last k MBConv blocks (+ head) get gradients, frozen ones
+    none, and the trained blocks' gradients equal those of the fully trainable run; .eval() afterwards uses the updated
+    running statistics through the folded eval kernels."""
+    from helpers import extractor_train_inputs
+    from mintime_b200 import EfficientNet
+    esd, x, probe = extractor_train_inputs()
+    grads = {}
+    for unfreeze in (16, 3):
+        ext = EfficientNet.from_name("efficientnet-b0", precision="fp32", drop_connect_rate=0.0)
+        ext.load_state_dict(esd)
+        ext = ext.to(DEV).train()
+        for name, p in ext.named_parameters():                           # train.py:159-167
+            if name.startswith("_blocks."):
+                p.requires_grad_(int(name.split(".")[1]) >= 16 - unfreeze)
+            else:
+                p.requires_grad_(unfreeze == 16 or name.startswith(("_conv_head", "_bn1")))
+        out = ext(x.to(DEV))
+        (out * probe.to(DEV)).sum().backward()
+        grads[unfreeze] = {k: (None if p.grad is None else p.grad.clone()) for k, p in ext.named_parameters()}
+    for k, g3 in grads[3].items():
+        blk = int(k.split(".")[1]) if k.startswith("_blocks.") else None
+        trainable = (blk is not None and blk >= 13) or k.startswith(("_conv_head", "_bn1"))
+        if trainable:
+            assert g3 is not None and rel_err(g3, grads[16][k]) <= 1e-6, k
+        else:
+            assert g3 is None, k
+    ext.eval()
+    with torch.no_grad():
+        e1 = ext(x.to(DEV))
+    ext2 = EfficientNet.from_name("efficientnet-b0", precision="fp32"); ext2.load_state_dict(esd); ext2 = ext2.to(DEV).eval()
+    with torch.no_grad():
+        e0 = ext2(x.to(DEV))
+    assert rel_err(e1, e0) > 1e-4                      # the running statistics moved (momentum 0.01)
+
+
+def test_features_gradient_reaches_the_extractor():
+    """train.py:347-355 with an unfrozen extractor: d loss / d features out of the transformer's backward (patch-embedding
+    data gradient) against the oracle's autograd (fp32 path)."""
+    cfg, tsd, meta, feats, labels, pw = grad_case_inputs("b3_f16_mixed_d2")
+    model = SizeInvariantTimeSformer(config=cfg, precision="fp32")
+    model.load_state_dict(tsd)
+    model = model.to(DEV).train()
+    fx = feats.to(DEV).requires_grad_(True)
+    y, loss = _step(model, cfg, meta, fx, labels, pw)
+    loss.backward()
+    fo = feats.clone().requires_grad_(True)
+    ol, _ = orc.tsf_forward({k: v for k, v in tsd.items()}, cfg, fo, meta["mask"], meta["identities_mask"], meta["size_embedding"],
+                            meta["positions"])
+    torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw]))(ol, labels).backward()
+    assert fx.grad is not None and fx.grad.shape == feats.shape
+    assert rel_err(fx.grad.cpu(), fo.grad) <= 2e-3
