@@ -92,18 +92,22 @@ class GraphedTrainStep:
     The eager step issues ~500 library launches plus ~400 small torch kernels from Python and is bound by that host
     work; the replay is bound by the GPU.  Everything the step does is capturable: the library never allocates or
     synchronises, the autograd node of ``training.py`` forks its weight-gradient GEMMs to side streams that join back
-    before it returns, the bf16 re-packing of the updated parameters is part of the captured forward, and SGD's foreach
-    update has no host dependency.  Fill ``static`` (videos, mask, identities_mask, size_embedding, positions, labels),
-    call ``replay()``; ``loss`` is the step's static output.  Single process only: the gradient exchange of a
-    data-parallel job (training.GradSync) is issued eagerly and is not captured.
+    before it returns, the bf16 re-packing of the updated parameters is part of the captured forward, and under data
+    parallelism the per-layer NCCL all-reduces of ``training.GradSync`` are captured with the backward that issues them
+    (NCCL collectives are graph-capturable; every rank captures the same sequence).  Fill ``static`` (videos, mask,
+    identities_mask, size_embedding, positions, labels), call ``replay()``; ``loss`` is the step's static output.
+
+    ``capture_optimizer`` (default False): ``optimizer.step()`` runs EAGERLY after every replay on the graph's static
+    gradient tensors, so learning-rate schedulers (train.py:380 calls ``lr_scheduler.step_update`` every iteration;
+    the shipped config uses a cosine schedule) and any optimizer work unchanged.  With True the update is captured too,
+    which freezes every host-side hyper-parameter (lr, weight decay) at its capture-time value: only for constant-lr SGD.
     """
 
     def __init__(self, extractor, model, optimizer, loss_fn, batch: int, num_frames: int, frame_dtype=torch.uint8,
-                 device="cuda:0", num_patches: int = 49, warmup: int = 3):
+                 device="cuda:0", num_patches: int = 49, warmup: int = 3, capture_optimizer: bool = False):
         self.device = torch.device(device)
         _lib.require_device(self.device)
-        if getattr(model, "_grad_sync", None) is not None:
-            raise ValueError("GraphedTrainStep captures a single-process step; detach the gradient exchange first")
+        self.capture_optimizer = capture_optimizer
         self.ext, self.model, self.opt, self.loss_fn = extractor, model, optimizer, loss_fn
         self.b, self.f = batch, num_frames
         d = self.device
@@ -134,7 +138,8 @@ class GraphedTrainStep:
             y = y[0]
         loss = self.loss_fn(y, s["labels"])
         loss.backward()
-        self.opt.step()
+        if self.capture_optimizer or self.graph is None:       # (the eager warm-up steps always update)
+            self.opt.step()
         return loss.detach(), y.detach()
 
     def capture(self):
@@ -148,15 +153,20 @@ class GraphedTrainStep:
                     self.opt.zero_grad(set_to_none=True)
                     self._step()
             torch.cuda.current_stream().wait_stream(side)
-            self.graph = torch.cuda.CUDAGraph()
+            graph = torch.cuda.CUDAGraph()
             self.opt.zero_grad(set_to_none=True)
             n0 = _lib.load().mt_prof_launch_count()
             # MINTIME_B200_TRAIN_PRIO=1: capture on a high-priority stream, so the kernel nodes of the critical path
             # outrank the weight-gradient work forked to the (default-priority) side streams
             import os
             cap = torch.cuda.Stream(priority=-1) if os.environ.get("MINTIME_B200_TRAIN_PRIO", "0") == "1" else None
-            with torch.cuda.graph(self.graph, stream=cap):
-                self.loss, self.logits = self._step()
+            self.graph = graph                                 # (set before the capture: _step skips the eager update)
+            try:
+                with torch.cuda.graph(graph, stream=cap):
+                    self.loss, self.logits = self._step()
+            except Exception:
+                self.graph = None
+                raise
             self.kernels_per_replay = int(_lib.load().mt_prof_launch_count() - n0)
         return self
 
@@ -164,4 +174,6 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture()
         self.graph.replay()
+        if not self.capture_optimizer:
+            self.opt.step()            # eager, on the graph's static .grad tensors: schedulers / any optimizer work
         return self.loss

@@ -97,7 +97,9 @@ class TrainPack:
 
 
 class GradSync:
-    """Bucketed (one bucket per layer) gradient all-reduce issued from inside the backward."""
+    """Bucketed (one flat fp32 bucket per layer + one for the small tensors) gradient all-reduce issued from inside the
+    backward; the buckets are averaged when the backward ends.  The collectives are plain ``dist.all_reduce`` calls
+    (NCCL on the GPU box, gloo in the CPU tests): under ``GraphedTrainStep`` they are captured with the backward."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -107,6 +109,8 @@ class GradSync:
         self.pending = []
 
     def launch(self, flat: torch.Tensor):
+        if not flat.is_contiguous():
+            raise ValueError("GradSync.launch: gradient buckets must be contiguous (a copy would never be handed to autograd)")
         if self.world > 1:
             self.pending.append((self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
 
@@ -117,9 +121,19 @@ class GradSync:
         self.pending = []
 
 
-def attach_grad_sync(model, group=None):
-    """Average the gradients over the ranks of `group` inside every backward of `model` (data parallel training)."""
+def attach_grad_sync(model, group=None, broadcast_parameters: bool = True):
+    """Average the gradients over the ranks of `group` inside every backward of `model` (data parallel training).
+    Like DistributedDataParallel, rank 0's parameters are broadcast first so the replicas start identical whatever each
+    rank seeded."""
     model._grad_sync = GradSync(group)
+    if broadcast_parameters and model._grad_sync.world > 1:
+        import torch.distributed as dist
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        with torch.no_grad():
+            for p in model.parameters():
+                dist.broadcast(p.data, src=src, group=group)
+        model._train_pack = None
+        model._packed = None
     return model
 
 
@@ -196,6 +210,9 @@ class TsfTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits, *_unused):
+        if ctx.saved is None:
+            raise RuntimeError("mintime_b200: the activations of this forward were released by its first backward "
+                               "(retain_graph=True is not supported: call forward again)")
         model, pk = ctx.model, ctx.pk
         precision = model.precision
         tok, mask_u8, idm_u8, se, pos = ctx.inputs
@@ -330,11 +347,16 @@ class TsfTrainFunction(torch.autograd.Function):
         if model.enable_size_emb:
             grads["size_emb.weight"] = dsize
         if sync is not None:
-            small = [grads[k] for k in ("to_out.1.weight", "to_out.1.bias", "to_out.0.weight", "to_out.0.bias",
-                                        "to_patch_embedding.weight", "to_patch_embedding.bias", "cls_token",
-                                        "pos_emb.weight") + (("size_emb.weight",) if model.enable_size_emb else ())]
-            for t in small:
-                sync.launch(t if t.is_contiguous() else t.contiguous())
+            # the tensors outside the layers travel as ONE flat bucket; the views handed to autograd alias it
+            names = ("to_out.1.weight", "to_out.1.bias", "to_out.0.weight", "to_out.0.bias", "to_patch_embedding.weight",
+                     "to_patch_embedding.bias", "cls_token", "pos_emb.weight") + (("size_emb.weight",) if model.enable_size_emb else ())
+            flat = torch.empty((sum(grads[k].numel() for k in names),), dtype=f32, device=dev)
+            off = 0
+            for k in names:
+                view, off = _carve(flat, off, tuple(grads[k].shape))
+                view.copy_(grads[k])
+                grads[k] = view
+            sync.launch(flat)
             sync.finish()
         ctx.saved = None
         out = [None] * ctx.n_extra

@@ -112,3 +112,44 @@ def test_grad_sync_averages_layer_buckets_over_ranks():
         assert r[1] == [1.5 * (i + 1) for i in range(3)]          # mean of (1, 2) * (i + 1)
         assert r[2] == [15.0 * (i + 1) for i in range(3)]
         assert r[3] == 0
+
+
+def _attach_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import mintime_b200  # noqa: F401
+    from mintime_b200 import SizeInvariantTimeSformer, training
+    from mintime_b200.spec import default_tsf_config
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = default_tsf_config(num_frames=8)
+    cfg["model"]["depth"] = 1
+    torch.manual_seed(100 + rank)                       # every rank initialises differently ...
+    model = SizeInvariantTimeSformer(config=cfg)
+    before = float(model.to_out[1].weight.double().sum())
+    training.attach_grad_sync(model)                    # ... and starts from rank 0's parameters, like DDP
+    after = float(model.to_out[1].weight.double().sum())
+    bad = None
+    try:
+        model._grad_sync.launch(torch.zeros(8, 8)[:, :4])
+    except ValueError as e:
+        bad = str(e)
+    q.put((rank, before, after, bad))
+    dist.destroy_process_group()
+
+
+def test_attach_grad_sync_broadcasts_rank0_parameters_and_rejects_copies():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_attach_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] != res[1][1]                       # different seeds
+    assert res[0][2] == res[1][2] == res[0][1]          # both hold rank 0's values afterwards
+    assert all("contiguous" in r[3] for r in res)

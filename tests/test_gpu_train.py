@@ -346,10 +346,12 @@ def test_graphed_train_step_matches_eager_steps():
         m = m.to(DEV).train()
         return m, torch.optim.SGD(m.parameters(), lr=0.01, weight_decay=1e-4)
 
-    # eager: 3 warm-up steps + 3 more
+    # eager: 3 warm-up steps + 3 more; the learning rate changes before step 5 (train.py:380 steps a scheduler per iteration)
     model, opt = make()
     eager = []
-    for _ in range(6):
+    for it in range(6):
+        if it == 4:
+            opt.param_groups[0]["lr"] = 0.002
         with torch.no_grad():
             feats = ext(frames.view(B * f, 224, 224, 3).permute(0, 3, 1, 2)).reshape(B, f, 1280, 7, 7)
         opt.zero_grad(set_to_none=True)
@@ -368,10 +370,18 @@ def test_graphed_train_step_matches_eager_steps():
     gs.static["labels"].copy_(labels)
     gs.capture()
     assert gs.kernels_per_replay > 150                       # extractor + 2-layer forward and backward, all in the graph
-    got = [gs.replay().item() for _ in range(3)]
+    got = []
+    for it in range(3):
+        if it == 1:
+            opt2.param_groups[0]["lr"] = 0.002               # takes effect: optimizer.step() runs eagerly after the replay
+        got.append(gs.replay().item())
     assert np.allclose(got, eager[3:], rtol=0, atol=2e-3), (got, eager)
     for (k, p), q in zip(model.named_parameters(), model2.parameters()):
         assert rel_err(q, p) <= 2e-3, k
+    # and the parameters did move with the new rate (a frozen lr of 0.01 would leave a 5x larger last update)
+    p0 = dict(model.named_parameters())["layers.0.2.fn.net.3.weight"]
+    q0 = dict(model2.named_parameters())["layers.0.2.fn.net.3.weight"]
+    assert rel_err(q0, p0) <= 1e-4
 
 
 def test_training_forward_returns_attention_maps_too():

@@ -142,8 +142,9 @@ def test_no_cpu_fallback():
         ops.layernorm_bwd_(torch.zeros(8, 512), torch.zeros(8, 512), torch.ones(512), torch.zeros(8, 512).bfloat16())
     with pytest.raises(_lib.MintimeError):
         ops.grad_prep(torch.zeros(64, 64), want_t=True)
-    e = EfficientNet.from_name("efficientnet-b0")      # train mode is not implemented: loud, not silent
-    with pytest.raises(NotImplementedError):
+    e = EfficientNet.from_name("efficientnet-b0")      # train mode (batch-stat BN, drop-connect, backward): no CPU route either
+    assert e.training
+    with pytest.raises(_lib.MintimeError):
         e(torch.zeros(1, 3, 224, 224))
 
 
