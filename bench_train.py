@@ -298,10 +298,10 @@ def run_train(args, emit, ClockSampler, load_peaks):
                                 "SizeInvariantTimeSformer forward + backward + SGD") + ", synthetic ForgeryNet-shaped clips",
                    "batch_per_gpu": B, "frames": f, "identities": ",".join(map(str, args.identities)),
                    "precision": args.precision + " compute, fp32 master weights and gradients",
-                   "launch": ("one CUDA-graph replay per step (GraphedTrainStep: extractor, forward, backward"
-                              + (", NCCL all-reduces" if world > 1 else "") + ") + eager optimizer.step()") if use_graph
+                   "launch": ("one CUDA-graph replay per step (GraphedTrainStep: extractor, forward, backward) + eager " + ("NCCL gradient exchange + " if world > 1 else "") + "optimizer.step()") if use_graph
                              else "eager nn.Module / autograd calls",
-                   "grad_exchange": "per-layer flat fp32 buckets, all-reduce issued inside the backward (NCCL), captured in the graph"
+                   "grad_exchange": ("per-layer flat fp32 buckets (9 x 29 MB + 1), NCCL all-reduce + average after the graph replay"
+                                     if use_graph else "per-layer flat fp32 buckets, NCCL all-reduce issued inside the backward")
                                     if world > 1 else "none (1 GPU)",
                    "timing": "CUDA events on the launch stream, max over ranks; activations per step (6.7 GB) exceed the L2"},
         "clocks": clocks,

@@ -92,10 +92,13 @@ class GraphedTrainStep:
     The eager step issues ~500 library launches plus ~400 small torch kernels from Python and is bound by that host
     work; the replay is bound by the GPU.  Everything the step does is capturable: the library never allocates or
     synchronises, the autograd node of ``training.py`` forks its weight-gradient GEMMs to side streams that join back
-    before it returns, the bf16 re-packing of the updated parameters is part of the captured forward, and under data
-    parallelism the per-layer NCCL all-reduces of ``training.GradSync`` are captured with the backward that issues them
-    (NCCL collectives are graph-capturable; every rank captures the same sequence).  Fill ``static`` (videos, mask,
-    identities_mask, size_embedding, positions, labels), call ``replay()``; ``loss`` is the step's static output.
+    before it returns, and the bf16 re-packing of the updated parameters is part of the captured forward.  Under data
+    parallelism (``training.attach_grad_sync``) the backward's gradient buckets are static tensors of the graph: the
+    replay is followed by ONE eager round of NCCL all-reduces over them (``GradSync.exchange``: 9 per-layer buckets of
+    29 MB + one small one) and the optimizer step.  (Capturing the collectives themselves was tried in round 2 and hung
+    at 2 GPUs inside the capture; the exchange is ~1 % of the step over NVLink, so it is issued after the replay.)
+    Fill ``static`` (videos, mask, identities_mask, size_embedding, positions, labels), call ``replay()``; ``loss`` is the
+    step's static output.
 
     ``capture_optimizer`` (default False): ``optimizer.step()`` runs EAGERLY after every replay on the graph's static
     gradient tensors, so learning-rate schedulers (train.py:380 calls ``lr_scheduler.step_update`` every iteration;
@@ -108,6 +111,8 @@ class GraphedTrainStep:
         self.device = torch.device(device)
         _lib.require_device(self.device)
         self.capture_optimizer = capture_optimizer
+        if capture_optimizer and getattr(model, "_grad_sync", None) is not None:
+            raise ValueError("capture_optimizer=True cannot be combined with a gradient exchange (it runs after the replay)")
         self.ext, self.model, self.opt, self.loss_fn = extractor, model, optimizer, loss_fn
         self.b, self.f = batch, num_frames
         d = self.device
@@ -127,6 +132,10 @@ class GraphedTrainStep:
 
     def _step(self):
         s = self.static
+        sync = getattr(self.model, "_grad_sync", None)
+        if sync is not None:
+            sync.deferred = self.graph is not None             # inside the capture: record the buckets, exchange later
+            sync.buckets = []
         with torch.no_grad():                                                              # train.py:344-346
             x = s["videos"].view(self.b * self.f, 224, 224, 3).permute(0, 3, 1, 2)
             feats = self.ext(x)
@@ -174,6 +183,9 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture()
         self.graph.replay()
+        sync = getattr(self.model, "_grad_sync", None)
+        if sync is not None:
+            sync.exchange()            # NCCL all-reduce + average of the graph's static gradient buckets
         if not self.capture_optimizer:
             self.opt.step()            # eager, on the graph's static .grad tensors: schedulers / any optimizer work
         return self.loss

@@ -107,11 +107,17 @@ class GradSync:
         self.group = group
         self.world = dist.get_world_size(group)
         self.pending = []
+        # deferred = True (set by GraphedTrainStep): the backward only RECORDS its buckets -- they are static tensors of
+        # the captured graph -- and exchange() all-reduces them after the replay, outside the capture
+        self.deferred = False
+        self.buckets = []
 
     def launch(self, flat: torch.Tensor):
         if not flat.is_contiguous():
             raise ValueError("GradSync.launch: gradient buckets must be contiguous (a copy would never be handed to autograd)")
-        if self.world > 1:
+        if self.deferred:
+            self.buckets.append(flat)
+        elif self.world > 1:
             self.pending.append((self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
 
     def finish(self):
@@ -119,6 +125,14 @@ class GradSync:
             work.wait()
             flat.mul_(1.0 / self.world)
         self.pending = []
+
+    def exchange(self):
+        """all-reduce + average the buckets a deferred backward recorded (call after the graph replay)"""
+        if self.world > 1:
+            works = [self.dist.all_reduce(b, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
+            for w, b in zip(works, self.buckets):
+                w.wait()
+                b.mul_(1.0 / self.world)
 
 
 def attach_grad_sync(model, group=None, broadcast_parameters: bool = True):

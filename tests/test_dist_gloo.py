@@ -90,7 +90,16 @@ def _grad_sync_worker(rank, world, port, q):
     for b in buckets:
         sync.launch(b)
     sync.finish()
-    q.put((rank, [float(b[0]) for b in buckets], [float(v.sum()) for v in views], len(sync.pending)))
+    # deferred mode (GraphedTrainStep): the backward only records its buckets, exchange() reduces them afterwards
+    sync.deferred = True
+    late = [torch.full((64,), float(rank + 1) * 10.0), torch.full((8,), float(rank))]
+    for b in late:
+        sync.launch(b)
+    sync.finish()
+    untouched = [float(b[0]) for b in late]
+    sync.exchange()
+    q.put((rank, [float(b[0]) for b in buckets], [float(v.sum()) for v in views], len(sync.pending), untouched,
+           [float(b[0]) for b in late]))
     dist.destroy_process_group()
 
 
@@ -112,6 +121,8 @@ def test_grad_sync_averages_layer_buckets_over_ranks():
         assert r[1] == [1.5 * (i + 1) for i in range(3)]          # mean of (1, 2) * (i + 1)
         assert r[2] == [15.0 * (i + 1) for i in range(3)]
         assert r[3] == 0
+        assert r[4] == [10.0 * (r[0] + 1), float(r[0])]             # nothing moved before exchange()
+        assert r[5] == [15.0, 0.5]                                   # mean over the two ranks afterwards
 
 
 def _attach_worker(rank, world, port, q):
