@@ -141,14 +141,15 @@ def run_reference(args, emit):
         from bench_train import cpu_train_videos_per_sec
         b = min(args.cpu_batch, 2)
         steps = max(1, min(args.steps, 3))
-        v, sec, cores = cpu_train_videos_per_sec(b, args.frames, args.identities, steps=steps)
-        sample = f"{b} clips x {args.frames} frames per training step, {steps} timed steps after 1 warm-up (bounded sample)"
+        v, sec, cores, kind = cpu_train_videos_per_sec(b, args.frames, args.identities, steps=steps)
+        sample = (f"{b} clips x {args.frames} frames per training step, {steps} timed steps after 1 warm-up (bounded sample), "
+                  + ("unmodified reference modules staged in oracle/_ref" if kind == "reference" else "oracle port"))
         emit({"impl": "reference", "metric": "train_videos_per_sec_16f_224px", "value": v, "unit": UNIT, "n_gpus": args.gpus,
               "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-              "config": {"workload": "BASELINE.json configs[3]: train.py step (frozen extractor), oracle on the host cores",
+              "config": {"workload": "BASELINE.json configs[3]: train.py step (frozen extractor) on the host cores",
                          "batch_per_gpu": args.batch, "frames": args.frames, "precision": "f32"},
-              "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+              "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
               "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
         return
     b = args.cpu_batch

@@ -11,19 +11,44 @@ import torch
 
 
 def cpu_train_videos_per_sec(batch, frames, identities, steps=2):
-    """The oracle's training step (extractor forward under no_grad + autograd through the transformer + SGD) on the host."""
+    """The reference's training step (train.py:332-378 with --freeze_backbone: extractor forward under no_grad + autograd
+    through the transformer + SGD) on the host cores: the UNMODIFIED reference modules staged in oracle/_ref when they are
+    there (kind "reference"), else the oracle port.  Returns (videos/s, s/step, threads, kind)."""
     from mintime_b200 import synth
     from mintime_b200.spec import default_tsf_config
     from oracle import mintime_oracle as orc
+    from oracle import ref_arm
     torch.set_num_threads(os.cpu_count())
     cfg = default_tsf_config(num_frames=frames)
-    esd = synth.make_effnet_state_dict(1234)
-    tsd = {k: v.clone().requires_grad_(True) for k, v in synth.make_tsf_state_dict(cfg, 4321).items()}
-    opt = torch.optim.SGD(list(tsd.values()), lr=0.01, weight_decay=1e-4)
+    esd = synth.make_effnet_state_dict(1234, conditioned=True)
     meta = synth.make_batch_meta(batch, frames, identities, seed=1234)
     clip = synth.make_frames(batch, frames, seed=1234, mask=meta["mask"])
     labels = (torch.arange(batch) % 2).float().view(batch, 1)
     lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([0.8169]))
+    if ref_arm.available():
+        from einops import rearrange
+        ext, model = ref_arm.build_modules(esd, synth.make_tsf_state_dict(cfg, 4321), cfg, require_attention=False)
+        model.train()
+        ropt = torch.optim.SGD(model.parameters(), lr=0.01, weight_decay=1e-4)
+
+        def rstep():
+            with torch.no_grad():                                       # train.py:344-346
+                feats = ext(rearrange(clip, "b f h w c -> (b f) c h w"))
+            feats = rearrange(feats, "(b f) c h w -> b f c h w", b=batch)
+            y = model(feats, mask=meta["mask"], size_embedding=meta["size_embedding"], identities_mask=meta["identities_mask"],
+                      positions=meta["positions"])
+            ropt.zero_grad()
+            lossf(y, labels).backward()
+            ropt.step()
+
+        rstep()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rstep()
+        sec = (time.perf_counter() - t0) / steps
+        return batch / sec, sec, torch.get_num_threads(), "reference"
+    tsd = {k: v.clone().requires_grad_(True) for k, v in synth.make_tsf_state_dict(cfg, 4321).items()}
+    opt = torch.optim.SGD(list(tsd.values()), lr=0.01, weight_decay=1e-4)
 
     def step():
         with torch.no_grad():
@@ -40,7 +65,7 @@ def cpu_train_videos_per_sec(batch, frames, identities, steps=2):
     for _ in range(steps):
         step()
     sec = (time.perf_counter() - t0) / steps
-    return batch / sec, sec, torch.get_num_threads()
+    return batch / sec, sec, torch.get_num_threads(), "port"
 
 
 class NvmlSampler:
@@ -120,7 +145,7 @@ def run_train(args, emit, ClockSampler, load_peaks):
     B, f = args.batch, args.frames
     cfg = default_tsf_config(num_frames=f)
     ext = mintime_b200.EfficientNet.from_name("efficientnet-b0", precision=args.precision)
-    ext.load_state_dict(synth.make_effnet_state_dict(1234))
+    ext.load_state_dict(synth.make_effnet_state_dict(1234, conditioned=True))
     ext = ext.to(dev).eval()                                            # train.py:153-154 (freeze_backbone)
     unfrozen = bool(getattr(args, "unfrozen", False))
     if unfrozen:                                                        # train.py:155-170
@@ -250,10 +275,11 @@ def run_train(args, emit, ClockSampler, load_peaks):
     lib.mt_prof_reset()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_train_videos_per_sec(2, f, args.identities)
-        cpu = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port",
-               "sample": f"2 clips x {f} frames per training step (oracle: extractor forward + torch autograd through the "
-                         f"fp32 restatement + SGD), 2 timed steps after 1 warm-up, {sec:.2f} s/step"}
+        v, sec, cores, kind = cpu_train_videos_per_sec(2, f, args.identities)
+        cpu = {"value": v, "unit": "videos/s", "cores": cores, "kind": kind,
+               "sample": f"2 clips x {f} frames per training step ("
+                         + ("unmodified reference modules staged in oracle/_ref" if kind == "reference" else "oracle port")
+                         + f": extractor forward under no_grad + torch autograd + SGD), 2 timed steps after 1 warm-up, {sec:.2f} s/step"}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -342,9 +342,10 @@ int mt_divided_attn_bwd(int precision, const void* qkv, const void* dout, const 
                         int dim_head, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the token build (:225-248) w.r.t. the embedding tables and the CLS token: g0 f32 [B][1+f*n][dim] is
- * scattered (+=, fp32 atomics) into dpos / dsize (table-shaped, may be NULL) and dcls [dim]; the caller zeroes them. */
+ * scattered (+=, fp32 atomics) into dpos / dsize ([table_rows][dim], may be NULL) and dcls [dim]; the caller zeroes them.
+ * An index outside [0, table_rows) traps the kernel (nn.Embedding raises IndexError), in the forward as well. */
 int mt_embed_bwd(const float* g0, const int64_t* positions, const int32_t* size_embedding, float* dpos, float* dsize,
-                 float* dcls, int batch, int f, int n, int dim, void* stream);
+                 float* dcls, int batch, int f, int n, int dim, int table_rows, void* stream);
 
 /* Backward of mt_head_fwd: gx[b][0][:] = dL/dx[b][0] (assigned; the other rows of gx are the caller's to zero);
  * grads f32 [classes*dim + classes + 2*dim] = (dW | dbias | dgamma | dbeta). */

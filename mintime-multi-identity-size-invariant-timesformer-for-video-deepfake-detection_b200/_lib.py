@@ -141,7 +141,7 @@ def load() -> C.CDLL:
     lib.mt_divided_attn_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.mt_divided_attn_bwd_workspace_bytes.restype = sz
     lib.mt_divided_attn_bwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, sz, vp]
-    lib.mt_embed_bwd.argtypes = [fp, vp, vp, fp, fp, fp, i32, i32, i32, i32, vp]
+    lib.mt_embed_bwd.argtypes = [fp, vp, vp, fp, fp, fp, i32, i32, i32, i32, i32, vp]
     lib.mt_head_bwd_workspace_bytes.argtypes = [i32, i32, i32]
     lib.mt_head_bwd_workspace_bytes.restype = sz
     lib.mt_head_bwd.argtypes = [fp, fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, vp, sz, vp]

@@ -132,6 +132,8 @@ struct EpiParams {
   const float* size_tab;
   const long long* positions;  // [B][rows_per_batch + 1] or null (-> arange)
   const int* size_idx;         // [B][f]
+  int table_rows;              // rows of pos_tab / size_tab: an index outside [0, table_rows) traps the kernel (nn.Embedding
+                               // raises IndexError in the reference; silently reading out of bounds is not an option)
 };
 
 struct GemmArgs {
@@ -181,12 +183,14 @@ __device__ __forceinline__ void epi_store8(const EpiParams& p, int row, int col,
     const int b = row / p.rows_per_batch, t = row - b * p.rows_per_batch;
     const size_t orow = (size_t)row + b + 1;
     const long long pos = p.positions ? p.positions[(size_t)b * (p.rows_per_batch + 1) + 1 + t] : (long long)(1 + t);
+    if ((unsigned long long)pos >= (unsigned long long)p.table_rows) __trap();
     float e[8];
     load8(p.pos_tab + (size_t)pos * p.ldo + col, e);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += e[i];
     if (p.size_tab) {
       const int si = p.size_idx[b * p.frames + t / p.n_patches];
+      if ((unsigned)si >= (unsigned)p.table_rows) __trap();
       load8(p.size_tab + (size_t)si * p.ldo + col, e);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] += e[i];

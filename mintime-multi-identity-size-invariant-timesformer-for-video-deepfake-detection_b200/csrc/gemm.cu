@@ -658,8 +658,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
           const int b = row / p.rows_per_batch, t = row - b * p.rows_per_batch;
           const size_t orow = (size_t)row + b + 1;
           const long long pos = p.positions ? p.positions[(size_t)b * (p.rows_per_batch + 1) + 1 + t] : (long long)(1 + t);
+          if ((unsigned long long)pos >= (unsigned long long)p.table_rows) __trap();
           v += p.pos_tab[(size_t)pos * p.ldo + col];
-          if (p.size_tab) v += p.size_tab[(size_t)p.size_idx[b * p.frames + t / p.n_patches] * p.ldo + col];
+          if (p.size_tab) {
+            const int si = p.size_idx[b * p.frames + t / p.n_patches];
+            if ((unsigned)si >= (unsigned)p.table_rows) __trap();
+            v += p.size_tab[(size_t)si * p.ldo + col];
+          }
           reinterpret_cast<float*>(p.out)[orow * p.ldo + col] = v;
         }
       }

@@ -258,9 +258,10 @@ __global__ void __launch_bounds__(128) attn_group_kernel(const T* __restrict__ q
 // x[b][0] = cls_token + pos_emb[positions[b][0]] + size_emb[0]   (:231-248)
 __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos_tab,
                                const float* __restrict__ size_tab, const long long* __restrict__ positions, float* x,
-                               int tokens, int dim) {
+                               int tokens, int dim, int table_rows) {
   const int b = blockIdx.x;
   const long long p = positions ? positions[(size_t)b * tokens] : 0;
+  if ((unsigned long long)p >= (unsigned long long)table_rows) __trap();     // nn.Embedding would raise IndexError
   for (int c = threadIdx.x; c < dim; c += blockDim.x) {
     float v = cls[c] + pos_tab[(size_t)p * dim + c];
     if (size_tab) v += size_tab[c];
@@ -496,13 +497,16 @@ extern "C" int mt_patch_embed_fwd(int precision, const mt_tsf_weights_t* w, cons
   const long long* pos = cfg->enable_pos_emb ? reinterpret_cast<const long long*>(positions) : nullptr;
   const float* size_tab = cfg->enable_size_emb ? w->size_emb : nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cls_row_kernel<<<batch, 128, 0, st>>>(w->cls_token, w->pos_emb, size_tab, pos, x, fn + 1, cfg->dim);
+  const int table_rows = cfg->num_frames * cfg->channels + 1;      // num_positions + 1 (:173-180)
+  MT_REQUIRE(fn + 1 <= table_rows, "patch_embed: %d tokens exceed the %d rows of the embedding tables", fn + 1, table_rows);
+  cls_row_kernel<<<batch, 128, 0, st>>>(w->cls_token, w->pos_emb, size_tab, pos, x, fn + 1, cfg->dim, table_rows);
   MT_LAUNCH_CHECK("cls_row_kernel");
   GemmArgs g{};
   g.a = feats; g.w = w->w_patch; g.M = batch * fn; g.N = cfg->dim; g.K = cfg->channels;
   g.epi.kind = EPI_PATCH_EMBED; g.epi.M = g.M; g.epi.N = g.N; g.epi.bias = w->b_patch; g.epi.out = x;
   g.epi.ldo = cfg->dim; g.epi.rows_per_batch = fn; g.epi.n_patches = cfg->num_patches; g.epi.frames = cfg->num_frames;
   g.epi.pos_tab = w->pos_emb; g.epi.size_tab = size_tab; g.epi.positions = pos; g.epi.size_idx = size_embedding;
+  g.epi.table_rows = table_rows;
   return launch_gemm(precision, g, st);
 }
 

@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const float* __restrict_
                                                         const long long* __restrict__ positions,
                                                         const int* __restrict__ size_idx, float* __restrict__ dpos,
                                                         float* __restrict__ dsize, float* __restrict__ dcls, int f, int n,
-                                                        int dim) {
+                                                        int dim, int table_rows) {
   const int b = blockIdx.x / (f + 1), fr = blockIdx.x % (f + 1);
   const int N = 1 + f * n;
   const float* gb = g0 + (size_t)b * N * dim;
@@ -638,6 +638,7 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const float* __restrict_
     if (fr == f) {
       const float v = gb[c];
       const long long p = positions ? positions[(size_t)b * N] : 0;
+      if ((unsigned long long)p >= (unsigned long long)table_rows) __trap();      // (the forward already trapped on it)
       if (dpos) atomicAdd(dpos + (size_t)p * dim + c, v);
       if (dsize) atomicAdd(dsize + c, v);
       atomicAdd(dcls + c, v);
@@ -647,10 +648,15 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const float* __restrict_
         const int tok = 1 + fr * n + t;
         const float v = gb[(size_t)tok * dim + c];
         const long long p = positions ? positions[(size_t)b * N + tok] : (long long)tok;
+        if ((unsigned long long)p >= (unsigned long long)table_rows) __trap();
         if (dpos) atomicAdd(dpos + (size_t)p * dim + c, v);
         acc += v;
       }
-      if (dsize) atomicAdd(dsize + (size_t)size_idx[b * f + fr] * dim + c, acc);
+      if (dsize) {
+        const int si = size_idx[b * f + fr];
+        if ((unsigned)si >= (unsigned)table_rows) __trap();
+        atomicAdd(dsize + (size_t)si * dim + c, acc);
+      }
     }
   }
 }
@@ -858,13 +864,13 @@ extern "C" int mt_divided_attn_bwd(int precision, const void* qkv, const void* d
 }
 
 extern "C" int mt_embed_bwd(const float* g0, const int64_t* positions, const int32_t* size_embedding, float* dpos,
-                            float* dsize, float* dcls, int batch, int f, int n, int dim, void* stream) {
-  MT_REQUIRE(g0 && dcls && batch > 0 && f > 0 && n > 0 && dim > 0, "embed_bwd: bad argument");
+                            float* dsize, float* dcls, int batch, int f, int n, int dim, int table_rows, void* stream) {
+  MT_REQUIRE(g0 && dcls && batch > 0 && f > 0 && n > 0 && dim > 0 && table_rows > f * n, "embed_bwd: bad argument");
   MT_REQUIRE(!dsize || size_embedding, "embed_bwd: dsize needs size_embedding");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ProfScope prof(st, 0.0, (double)batch * (1 + f * n) * dim * 12.0, "embed_bwd");
   embed_bwd_kernel<<<batch * (f + 1), 128, 0, st>>>(g0, reinterpret_cast<const long long*>(positions), size_embedding, dpos,
-                                                    dsize, dcls, f, n, dim);
+                                                    dsize, dcls, f, n, dim, table_rows);
   MT_LAUNCH_CHECK("embed_bwd_kernel");
   return MT_OK;
 }

@@ -332,7 +332,7 @@ def embed_bwd(g0, positions, size_embedding, table_rows: int, f: int, n: int, wa
     dcls = torch.zeros((dim,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.load().mt_embed_bwd(g0.data_ptr(), _lib.ptr(positions), _lib.ptr(size_embedding), _lib.ptr(dpos),
-                                      _lib.ptr(dsize), dcls.data_ptr(), B, f, n, dim, _lib.stream_ptr())
+                                      _lib.ptr(dsize), dcls.data_ptr(), B, f, n, dim, table_rows, _lib.stream_ptr())
     _lib.check(rc, "mt_embed_bwd")
     return dpos, dsize, dcls
 

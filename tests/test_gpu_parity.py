@@ -14,6 +14,8 @@ Tolerances
               torch.autocast(cpu, bf16) vs its own fp32: logits up to 0.087, maps up to 0.094 rel-L2,
               features 0.42 rel-L2).  Bars: logits |err| <= 0.1, maps rel-L2 <= 0.15.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -805,3 +807,34 @@ def test_graphed_hot_path():
                                   positions=meta["positions"].to(DEV))
         torch.cuda.synchronize()
         assert torch.equal(got[0], le) and torch.equal(got[1], se_) and torch.equal(got[2], te)
+
+
+@pytest.mark.gpu
+def test_out_of_range_embedding_index_fails_loudly():
+    """nn.Embedding raises IndexError on a bad index (size_invariant_timesformer.py:235-248); the kernels trap instead of
+    reading / scattering out of bounds.  A trap poisons the CUDA context, so this runs in its own process."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import mintime_b200
+from mintime_b200 import SizeInvariantTimeSformer, synth
+from mintime_b200.spec import default_tsf_config
+cfg = default_tsf_config(num_frames=8)
+cfg["model"]["depth"] = 1
+m = SizeInvariantTimeSformer(config=cfg).to("cuda:0").eval()
+meta = synth.make_batch_meta(1, 8, [1], seed=1)
+pos = meta["positions"].clone()
+pos[0, 5] = 8 * 1280 + 1                       # one past the last row of pos_emb
+try:
+    with torch.no_grad():
+        y = m(torch.zeros(1, 8, 1280, 7, 7, device="cuda:0"), mask=meta["mask"].cuda(), size_embedding=meta["size_embedding"],
+              identities_mask=meta["identities_mask"].cuda(), positions=pos.cuda())
+    torch.cuda.synchronize()
+    print("NO ERROR", float(y.sum()))
+except Exception as e:
+    print("RAISED", type(e).__name__)
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "RAISED" in r.stdout and "NO ERROR" not in r.stdout, (r.stdout, r.stderr[-500:])
