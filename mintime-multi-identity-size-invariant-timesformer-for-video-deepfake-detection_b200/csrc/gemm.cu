@@ -814,11 +814,25 @@ bool tc2_enabled() {
   return on == 1;
 }
 
+// MINTIME_B200_NO_TC2A=1 (read once): keep the streaming pair kernel for the K = 512 contractions (A/B measurements)
+bool tc2a_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MINTIME_B200_NO_TC2A");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 template <int KIND, bool GATED>
 int launch_tc(const GemmArgs& g, cudaStream_t stream) {
   if constexpr (!GATED && (KIND == EPI_STORE || KIND == EPI_GEGLU || KIND == EPI_RESID_F32)) {
     // large transformer contractions: CTA-pair kernel (256x256 tiles, cta_group::2)
-    if (tc2_enabled() && g.splits <= 1 && tc2_eligible(g)) return launch_tc2<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
+    if (tc2_enabled() && g.splits <= 1 && tc2_eligible(g)) {
+      if constexpr (KIND != EPI_RESID_F32) {
+        if (tc2a_enabled() && tc2a_eligible(g)) return launch_tc2a<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
+      }
+      return launch_tc2<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
+    }
   }
   // per-row gathers (skip connection, embedding rows) use the direct epilogue; everything else TMA
   if (KIND == EPI_PATCH_EMBED) return launch_tc_impl<KIND, GATED, false>(g, stream);
