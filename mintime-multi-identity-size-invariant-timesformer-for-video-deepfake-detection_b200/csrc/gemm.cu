@@ -43,7 +43,8 @@ struct TcParams {
   int tmem_cols;    // power of two >= acc_stages * block_n
   int acc_stages;   // TMEM accumulator buffers (2, or 1 when two CTAs share the SM's 512 columns at block_n > 128)
   int gate_imgs;    // > 0: SE gate rows of up to this many images are staged in smem per tile (GATED)
-  int b_resident;   // 1: the whole weight matrix (one column tile, all k-blocks) is loaded into smem once per block
+  int b_resident;   // 1: the block's weight slice (one column tile, all k-blocks) is loaded into smem once per block
+  int n_outer;      // 1: 2-D grid, blockIdx.y = the block's (fixed) column tile, blockIdx.x strides over the row tiles
   int splits;       // split-K (EPI_RESID_F32 through the TMA reduce-add only): every output tile is worked on by
   int kb_per_split; // `splits` tiles, each over kb_per_split k-blocks; the cp.reduce .add epilogue sums them in L2
   const float* gate;
@@ -119,6 +120,53 @@ constexpr int epi_warps() { return (KIND == EPI_STORE && TMA_OUT) ? 8 : 4; }
 template <int KIND, bool GATED, bool TMA_OUT>
 constexpr int tc_threads() { return 64 + 32 * epi_warps<KIND, TMA_OUT>() + (GATED ? 128 : 0); }
 
+// One 32-row x 32-column unit of the 8-warp bf16 epilogue: accumulator registers -> BN shift (+ swish) (+ skip row) ->
+// bf16 -> the warp's staging slab (64-byte swizzle: 16-byte piece g of row `lane` sits at piece g ^ ((lane >> 1) & 3)).
+// ACT / RES / FULL are compile-time so that the unit is straight-line code; the arithmetic is the library's one
+// swish form (h = x/2 + shift/2, h + h*tanh(h); bias_c holds the pre-halved shift when ACT).
+template <bool ACT, bool RES, bool FULL>
+__device__ __forceinline__ void epi8_unit(const uint32_t (&r)[32], const float* bias_c, const bf16* rrow, int groups,
+                                          uint8_t* stg, int lane) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float2 v[4];
+    if (FULL || g < groups) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_c + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_c + g * 8 + 4);
+      const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                            make_float2(b1.z, b1.w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1]));
+        if (ACT) {
+          const float2 h = __ffma2_rn(x, make_float2(0.5f, 0.5f), bb[i]);
+          float2 t;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+          v[i] = __ffma2_rn(h, t, h);
+        } else {
+          v[i] = __fadd2_rn(x, bb[i]);
+        }
+      }
+      if (RES) {
+        if (rrow != nullptr) {                       // MBConv skip connection (model.py:123-127), added after BN
+          const uint4 q = *reinterpret_cast<const uint4*>(rrow + g * 8);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[i] = __fadd2_rn(v[i], make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u)));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = make_float2(0.f, 0.f);
+    }
+    *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y),
+                   pack_bf16(v[3].x, v[3].y));
+  }
+}
+
 template <int N>
 __device__ __forceinline__ void bar_sync_epi_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
@@ -128,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_out, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [A stages][B stages][2 staging buffers (TMA_OUT)][barriers][tmem ptr]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; stays a shared-space pointer (LDS/STS, not generic LD/ST)
   const int b_stage_bytes = p.block_n * kBlockK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages * kAStageBytes;
@@ -157,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
-      ptx::mbar_init(&gated_bar[s], 128);
+      ptx::mbar_init(&gated_bar[s], 4);       // one arrival per gate warp
     }
     ptx::mbar_init(b_full, 1);
     for (int s = 0; s < 2; ++s) {
@@ -183,6 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int mn_tiles = p.tiles_m * p.tiles_n;
   const int num_tiles = mn_tiles * p.splits;      // tile = split * mn_tiles + (m-tile, n-tile)
+  // tile walk: grid-stride over all tiles, or (n_outer) a fixed column tile per block (blockIdx.y) with a stride over
+  // the row tiles, so that the block's weight slice can stay in shared memory
+  const int tile0 = p.n_outer ? (int)blockIdx.x * p.tiles_n + (int)blockIdx.y : (int)blockIdx.x;
+  const int tstep = p.n_outer ? (int)gridDim.x * p.tiles_n : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -194,10 +246,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (p.b_resident) {
         ptx::mbar_arrive_expect_tx(b_full, (uint32_t)(num_kb * b_stage_bytes));
         for (int kb = 0; kb < num_kb; ++kb)
-          ptx::tma_load_2d(smem_b + kb * b_stage_bytes, &tmap_b, b_full, kb * kBlockK, 0);
+          ptx::tma_load_2d(smem_b + kb * b_stage_bytes, &tmap_b, b_full, kb * kBlockK, (int)blockIdx.y * p.block_n);
       }
       const uint32_t tx_bytes = (uint32_t)(kAStageBytes + (p.b_resident ? 0 : b_stage_bytes));
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int split = tile / mn_tiles, t2 = tile - split * mn_tiles;
         const int m0 = (t2 / p.tiles_n) * kBlockM;
         const int n0 = (t2 % p.tiles_n) * p.block_n;
@@ -220,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t idesc = ptx::umma_idesc_bf16_f32(kBlockM, (uint32_t)p.block_n);
       if (p.b_resident) ptx::mbar_wait(b_full, 0);
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
         const int as = p.acc_stages == 2 ? (it & 1) : 0;
         const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -263,7 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int n_units = (p.block_n + 31) >> 5;
     uint32_t store_it = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
       const int as = p.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
       if (p.acc_stages == 2 && as != half) continue;
@@ -275,50 +327,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
       const int u0 = p.acc_stages == 2 ? 0 : ((half + it) & 1), ustep = p.acc_stages == 2 ? 1 : 2;
-      for (int u = u0; u < n_units; u += ustep) {
+      const int units_here = min(n_units, (p.N - n0 + 31) >> 5);     // the last column tile may be narrower
+      for (int u = u0; u < units_here; u += ustep) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(taddr + u * 32, r);
         uint8_t* stg = slab + (store_it & 1) * 2048;
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab's previous store drained
         __syncwarp();
-        ptx::tmem_ld_wait();
         const int col = n0 + u * 32;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float2 v[4];
-          if (col + g * 8 < p.N) {                 // (N is a multiple of 8)
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col + g * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + g * 8 + 4);
-            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
-                                  make_float2(b1.z, b1.w)};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 x = make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1]));
-              if (act) {                           // swish(x + shift): h = x/2 + shift/2, h + h*tanh(h)
-                const float2 h = __ffma2_rn(x, make_float2(0.5f, 0.5f), bb[i]);
-                float2 t;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
-                v[i] = __ffma2_rn(h, t, h);
-              } else {
-                v[i] = __fadd2_rn(x, bb[i]);
-              }
-            }
-            if (resid != nullptr && row < p.M) {    // MBConv skip connection (model.py:123-127), added after BN
-              const uint4 q = *reinterpret_cast<const uint4*>(resid + (size_t)row * e.ldo + col + g * 8);
-              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                v[i] = __fadd2_rn(v[i], make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u)));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = make_float2(0.f, 0.f);
-          }
-          // 64-byte swizzle: 16-byte piece g of row `lane` sits at piece g ^ ((lane >> 1) & 3)
-          *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-              make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y),
-                         pack_bf16(v[3].x, v[3].y));
+        const int groups = min(4, (p.N - col) >> 3);                 // valid 8-column groups (N is a multiple of 8)
+        const bf16* rrow = (resid != nullptr && row < p.M) ? resid + (size_t)row * e.ldo + col : nullptr;
+        // one warp-uniform dispatch per unit instead of per-element predicates (the epilogue is issue bound)
+        const int variant = (act ? 4 : 0) | (resid != nullptr ? 2 : 0) | (groups == 4 ? 1 : 0);
+        ptx::tmem_ld_wait();
+        switch (variant) {
+          case 0: epi8_unit<false, false, false>(r, bias_s + col, rrow, groups, stg, lane); break;
+          case 1: epi8_unit<false, false, true>(r, bias_s + col, rrow, groups, stg, lane); break;
+          case 2: epi8_unit<false, true, false>(r, bias_s + col, rrow, groups, stg, lane); break;
+          case 3: epi8_unit<false, true, true>(r, bias_s + col, rrow, groups, stg, lane); break;
+          case 4: epi8_unit<true, false, false>(r, bias_s + col, rrow, groups, stg, lane); break;
+          case 5: epi8_unit<true, false, true>(r, bias_s + col, rrow, groups, stg, lane); break;
+          case 6: epi8_unit<true, true, false>(r, bias_s + col, rrow, groups, stg, lane); break;
+          default: epi8_unit<true, true, true>(r, bias_s + col, rrow, groups, stg, lane); break;
         }
         ptx::fence_proxy_async_smem();             // slab writes -> visible to the TMA engine
         __syncwarp();
@@ -344,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const EpiParams& e = p.epi;
     uint32_t store_it = 0;                         // staging buffer ring position (TMA_OUT)
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
       const int as = p.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t aphase = (p.acc_stages == 2 ? (it >> 1) : it) & 1;
       const int t2 = tile % mn_tiles;
@@ -485,7 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // per tile with coalesced loads, so the TMA -> gate -> MMA critical path holds no global-memory latency.
     const int r = threadIdx.x - kGateThread0;  // tile row 0..127
     PipeState ps;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m0 = ((tile % mn_tiles) / p.tiles_n) * kBlockM;
       const int row = m0 + r;
       const int img = (row < p.M ? row : p.M - 1) / p.rows_per_gate;
@@ -510,14 +540,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       for (int kb = 0; kb < num_kb; ++kb) {
         if (gsm) {
-          ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
-          uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
+          // all loads of the row first, then the multiplies, then the stores: the A tile and the gate rows are both
+          // shared memory, so an interleaved form serialises on possible aliasing (8 dependent round trips per stage)
           const bf16* gk = gsm + kb * kBlockK;
+          const int valid = min(8, (p.K - kb * kBlockK) >> 3);      // 16-byte pieces inside K (K % 8 == 0 here)
+          // (two batches of four pieces: the block runs at 72 registers per thread; the full k-block is straight-line
+          // code -- per-piece guards made the compiler rematerialise the addresses (S2R/S2UR) in every piece)
+          uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
+          const uint32_t sw = (uint32_t)(r & 7) << 4;
+          if (valid == 8) {
+            uint4 gq[4], u[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (kb * kBlockK + c * 8 < p.K) {
+            for (int c = 0; c < 4; ++c) gq[c] = *reinterpret_cast<const uint4*>(gk + c * 8);
+            ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) u[c] = *reinterpret_cast<const uint4*>(arow + (((half * 4 + c) << 4) ^ sw));
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u[c]);
+                const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[c]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __hmul2(h[i], gh[i]);
+              }
+              if (half == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) gq[c] = *reinterpret_cast<const uint4*>(gk + (4 + c) * 8);
+              }
+#pragma unroll
+              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(arow + (((half * 4 + c) << 4) ^ sw)) = u[c];
+            }
+          } else {
+            ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
+            for (int c = 0; c < valid; ++c) {                       // K tail (one k-block per tile at most)
               const uint4 gq = *reinterpret_cast<const uint4*>(gk + c * 8);
-              uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
+              uint4* ptr = reinterpret_cast<uint4*>(arow + ((uint32_t)(c << 4) ^ sw));
               uint4 u = *ptr;
               __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
               const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq);
@@ -527,7 +585,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&gated_bar[ps.stage]);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&gated_bar[ps.stage]);
           ps.advance(p.stages);
           continue;
         }
@@ -562,7 +621,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&gated_bar[ps.stage]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&gated_bar[ps.stage]);
         ps.advance(p.stages);
       }
     }
@@ -717,6 +777,15 @@ int make_tmap_2d(CUtensorMap* m, const void* base, bool f32, int rows, int cols,
 
 int num_sms() { return current_sms(); }
 
+// largest weight slice kept resident by a one-block-per-SM launch (MINTIME_B200_WRES_KB, read once; 0 disables)
+int wres_limit_bytes() {
+  static const int v = [] {
+    const char* e = getenv("MINTIME_B200_WRES_KB");
+    return std::min(e ? atoi(e) : 136, 136) * 1024;     // 136 KiB + staging/bias + 3 A stages = the 226 KiB budget
+  }();
+  return v;
+}
+
 template <int KIND, bool GATED, bool TMA_OUT>
 int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   TcParams p;
@@ -740,6 +809,19 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   const int num_kb = (g.K + kBlockK - 1) / kBlockK;
   const int b_block = bn * kBlockK * 2;
   p.b_resident = (p.tiles_n == 1 && num_kb * b_block <= 40 * 1024) ? 1 : 0;
+  p.n_outer = 0;
+  // Wide layers with several k-blocks run one block per SM (below) and were bound by re-streaming the weight slice
+  // for every 128-row tile (L2 -> SM: e.g. N=1152 K=192 moves 98 KB of W next to 49 KB of A per tile).  Give each
+  // block ONE column tile (2-D grid) and keep that slice in shared memory when it fits beside >= 3 A stages and the
+  // block has at least two row tiles to use it for.
+  if (KIND == EPI_STORE && TMA_OUT && bn > 128 && num_kb > 1 && g.splits <= 1 && !p.b_resident) {
+    const int res_limit = wres_limit_bytes();
+    const int gx = std::max(1, num_sms() / p.tiles_n);
+    if (num_kb * b_block <= res_limit && p.tiles_m >= 2 * gx) {
+      p.b_resident = 1;
+      p.n_outer = p.tiles_n > 1 ? 1 : 0;
+    }
+  }
   // split-K: only where partial tiles can be summed by the epilogue itself (fp32 TMA reduce-add, no bias)
   p.splits = 1;
   p.kb_per_split = num_kb;
@@ -796,8 +878,9 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gemm_tc)");
   }
-  int grid = p.tiles_m * p.tiles_n * p.splits;
-  if (grid > num_sms() * ctas_per_sm) grid = num_sms() * ctas_per_sm;
+  dim3 grid(p.tiles_m * p.tiles_n * p.splits);
+  if ((int)grid.x > num_sms() * ctas_per_sm) grid.x = num_sms() * ctas_per_sm;
+  if (p.n_outer) grid = dim3(std::min(p.tiles_m, std::max(1, num_sms() * ctas_per_sm / p.tiles_n)), p.tiles_n);
   kern<<<grid, tc_threads<KIND, GATED, TMA_OUT>(), smem, stream>>>(ta, tb, tout, p);
   MT_LAUNCH_CHECK("gemm_tc_kernel");
   return MT_OK;

@@ -139,7 +139,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   constexpr int kGroups = EPI_WARPS / 4;           // epilogue warp groups (each owns 2 staging buffers)
   constexpr int kStages2 = stages2(EPI_WARPS);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages2 * kAStageBytes;
   uint8_t* smem_stage = smem_b + kStages2 * kAStageBytes;
@@ -283,7 +283,7 @@ gemm_tc2a_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   constexpr int kGroups = EPI_WARPS / 4;
   constexpr int kResBStages = res_b_stages(EPI_WARPS);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* smem_a = smem;                                          // [kResKB][128 x 64]
   uint8_t* smem_b = smem_a + kResKB * kAStageBytes;                // [kResBStages][128 x 64]
   uint8_t* smem_stage = smem_b + kResBStages * kAStageBytes;       // [kGroups][128 x 128 B]

@@ -12,7 +12,8 @@ def r(*shape, scale=1.0, dtype=torch.bfloat16):
 cases = [(112 * 112, 16, 96, 0, 1, 0), (56 * 56, 24, 144, 0, 1, 0), (28 * 28, 40, 240, 0, 1, 0), (112 * 112, 32, 16, 1, 0, 0),
          (56 * 56, 144, 24, 1, 0, 1), (14 * 14, 112, 672, 0, 1, 0), (49, 1152, 192, 1, 0, 1), (14 * 14, 672, 112, 1, 0, 1),
          (14 * 14, 480, 80, 1, 0, 1), (49, 1152, 320, 1, 0, 0), (49, 192, 1152, 0, 1, 0), (14 * 14, 80, 480, 0, 1, 0),
-         (49, 1152, 192, 0, 0, 1), (49, 1152, 192, 0, 0, 0), (49, 1152, 192, 1, 0, 0), (14 * 14, 672, 112, 0, 0, 0)]
+         (49, 1152, 192, 0, 0, 1), (49, 1152, 192, 0, 0, 0), (49, 1152, 192, 1, 0, 0), (14 * 14, 672, 112, 0, 0, 0),
+         (49, 320, 1280, 0, 1, 0)]
 only = os.environ.get("ONLY")
 n_img = 512
 for ci, (hw, K, N, gated, act, res) in enumerate(cases):

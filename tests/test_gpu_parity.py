@@ -61,6 +61,9 @@ def tol(p, fp32=2e-5, bf16=1e-2):
     (40000, 16, 32, 0, False),      # block-0 project: narrowest tile, many row tiles (persistent loop)
     (4500, 512, 320, 1, False),     # CTA-pair (cta_group::2) kernel: 256x256 tiles, ragged M, K tail-free
     (25120, 1536, 512, 0, False),   # to_qkv at the bench size (CTA-pair kernel, 99 x 6 tiles over 74 pairs)
+    (25001, 1152, 192, 1, False),   # late-block expand: column tile fixed per block, weight slice resident (5 x 29 blocks)
+    (13000, 672, 112, 1, False),    # same walk with 3 column tiles (last one 160 wide), ragged M, K tail
+    (20011, 480, 80, 1, True),      # 2 column tiles + skip add
 ])
 def test_pointwise(prec, m, n, k, act, res):
     a = rnd((m, k), 1).to(T(prec)); w = rnd((n, k), 2, k ** -0.5).to(T(prec))
