@@ -539,85 +539,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         gsm = gs + (size_t)(img - img0) * p.K;
       }
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (gsm) {
-          // all loads of the row first, then the multiplies, then the stores: the A tile and the gate rows are both
-          // shared memory, so an interleaved form serialises on possible aliasing (8 dependent round trips per stage)
-          const bf16* gk = gsm + kb * kBlockK;
-          const int valid = min(8, (p.K - kb * kBlockK) >> 3);      // 16-byte pieces inside K (K % 8 == 0 here)
-          // (two batches of four pieces: the block runs at 72 registers per thread; the full k-block is straight-line
-          // code -- per-piece guards made the compiler rematerialise the addresses (S2R/S2UR) in every piece)
-          uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
-          const uint32_t sw = (uint32_t)(r & 7) << 4;
-          if (valid == 8) {
-            uint4 gq[4], u[4];
+        // Gates as packed bf16 (staged in shared memory, or -- single k-block shapes -- read from the fp32 gate row
+        // in global memory and packed here), one HMUL2 per channel pair.  Per half k-block (4 x 16 bytes of the row):
+        // all loads first, then the multiplies, then the stores -- the A tile and the staged gates are both shared
+        // memory, so an interleaved form serialises on possible aliasing; straight-line code for full halves (per-piece
+        // guards made the compiler rematerialise the addresses in every piece).  72 registers per thread.
+        const int valid = min(8, (p.K - kb * kBlockK) >> 3);       // 16-byte pieces inside K (K % 8 == 0)
+        const bf16* gk = gsm ? gsm + kb * kBlockK : nullptr;
+        const float* gf = grow + kb * kBlockK;
+        auto gate_piece = [&](int c) -> uint4 {
+          if (gk) return *reinterpret_cast<const uint4*>(gk + c * 8);
+          const float4 g0 = *reinterpret_cast<const float4*>(gf + c * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(gf + c * 8 + 4);
+          return make_uint4(pack_bf16(g0.x, g0.y), pack_bf16(g0.z, g0.w), pack_bf16(g1.x, g1.y), pack_bf16(g1.z, g1.w));
+        };
+        uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
+        const uint32_t sw = (uint32_t)(r & 7) << 4;
+        uint4 gq[4], u[4];
+        if (valid >= 4) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) gq[c] = *reinterpret_cast<const uint4*>(gk + c * 8);
-            ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
+          for (int c = 0; c < 4; ++c) gq[c] = gate_piece(c);       // before the wait: overlaps the TMA's latency
+        }
+        ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 2; ++half) {
+          const int nv = valid - half * 4;                          // pieces of this half inside K
+          if (nv >= 4) {
+            if (half == 1) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) u[c] = *reinterpret_cast<const uint4*>(arow + (((half * 4 + c) << 4) ^ sw));
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u[c]);
-                const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[c]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) h[i] = __hmul2(h[i], gh[i]);
-              }
-              if (half == 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) gq[c] = *reinterpret_cast<const uint4*>(gk + (4 + c) * 8);
-              }
-#pragma unroll
-              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(arow + (((half * 4 + c) << 4) ^ sw)) = u[c];
+              for (int c = 0; c < 4; ++c) gq[c] = gate_piece(4 + c);
             }
-          } else {
-            ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
-            for (int c = 0; c < valid; ++c) {                       // K tail (one k-block per tile at most)
-              const uint4 gq = *reinterpret_cast<const uint4*>(gk + c * 8);
-              uint4* ptr = reinterpret_cast<uint4*>(arow + ((uint32_t)(c << 4) ^ sw));
-              uint4 u = *ptr;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) u[c] = *reinterpret_cast<const uint4*>(arow + (((half * 4 + c) << 4) ^ sw));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u[c]);
+              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[c]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) h[i] = __hmul2(h[i], gh[i]);
-              *ptr = u;
             }
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&gated_bar[ps.stage]);
-          ps.advance(p.stages);
-          continue;
-        }
-        const float* gk = grow + kb * kBlockK;
-        // gates not staged (single k-block shapes): fetch the first half of the row's gates BEFORE waiting for the
-        // TMA so that their L2 latency overlaps the load
-        float4 pre[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (kb * kBlockK + c * 8 < p.K) {
-            pre[2 * c] = *reinterpret_cast<const float4*>(gk + c * 8);
-            pre[2 * c + 1] = *reinterpret_cast<const float4*>(gk + c * 8 + 4);
-          }
-        ptx::mbar_wait(&full_bar[ps.stage], ps.phase);
-        uint8_t* arow = smem_a + ps.stage * kAStageBytes + r * 128;
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(arow + (((half * 4 + c) << 4) ^ sw)) = u[c];
+          } else {
+            for (int c = 0; c < nv; ++c) {                          // K tail (at most one half per tile)
+              const uint4 g1 = gate_piece(half * 4 + c);
+              uint4* ptr = reinterpret_cast<uint4*>(arow + ((uint32_t)((half * 4 + c) << 4) ^ sw));
+              uint4 v = *ptr;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+              const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g1);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int k = kb * kBlockK + c * 8;
-          if (k < p.K) {
-            const bool use_pre = c < 4;
-            const float4 g0 = use_pre ? pre[2 * (c & 3)] : *reinterpret_cast<const float4*>(gk + c * 8);
-            const float4 g1 = use_pre ? pre[2 * (c & 3) + 1] : *reinterpret_cast<const float4*>(gk + c * 8 + 4);
-            uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4));
-            uint4 u = *ptr;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-            float2 f;
-            f = __bfloat1622float2(h[0]); h[0] = __floats2bfloat162_rn(f.x * g0.x, f.y * g0.y);
-            f = __bfloat1622float2(h[1]); h[1] = __floats2bfloat162_rn(f.x * g0.z, f.y * g0.w);
-            f = __bfloat1622float2(h[2]); h[2] = __floats2bfloat162_rn(f.x * g1.x, f.y * g1.y);
-            f = __bfloat1622float2(h[3]); h[3] = __floats2bfloat162_rn(f.x * g1.z, f.y * g1.w);
-            *ptr = u;
+              for (int i = 0; i < 4; ++i) h[i] = __hmul2(h[i], gh[i]);
+              *ptr = v;
+            }
           }
         }
         ptx::fence_proxy_async_smem();
