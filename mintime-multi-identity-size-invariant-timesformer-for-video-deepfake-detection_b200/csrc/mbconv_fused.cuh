@@ -163,6 +163,7 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   const int my_steps = (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int IW = g.d.IW;
   const int acc_cols = g.MB * CW;                        // TMEM columns of one accumulator buffer
+  const uint32_t iw_magic = (1u << 20) / (uint32_t)IW + 1u;   // row / IW == (row * iw_magic) >> 20 for row < 4096
 
   auto tile_origin = [&](int step, int& img, int& t, int& x0, int& y0) {
     const int work = blockIdx.x + step * gridDim.x;
@@ -249,40 +250,68 @@ mbconv_front_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       ptx::mbar_wait(&t_full[s], ph);
       ptx::tc_fence_after();
       uint8_t* exp_tile = exp_buf + s * g.exp_bytes;
-      for (int mb = half; mb < g.MB; mb += nd >> 2) {
+      // Software pipeline over this warp's 128-pixel blocks: the tcgen05.ld of the NEXT block is in flight while the
+      // current one goes through the swish (one block = 32 elements per lane = 256 MUFU cycles of the sub-partition;
+      // an exposed TMEM round trip per block cost about as much again).
+      const int mstep = nd >> 2;
+      const uint32_t tquad = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * acc_cols);
+      auto ld_block = [&](uint32_t (&r)[CW / 16][16], int mb) {
+#pragma unroll
+        for (int c16 = 0; c16 < CW / 16; ++c16) ptx::tmem_ld_32x32b_x16(tquad + (uint32_t)(mb * CW + c16 * 16), r[c16]);
+      };
+      auto release_tmem = [&]() {                          // this warp's last TMEM read of the tile has completed
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&t_empty[s]);
+      };
+      auto swish_block = [&](const uint32_t (&r)[CW / 16][16], int mb) {
         const int row = mb * 128 + quad * 32 + lane;     // pixel of the input tile
-        const int iy = row / IW, ix = row - iy * IW;
+        if (row >= g.n_pix) return;
+        const int iy = (int)(((uint32_t)row * iw_magic) >> 20), ix = row - iy * IW;     // row / IW (row < 4096)
         const int gy = y0 + iy, gx = x0 + ix;
         const bool in_img = gy >= 0 && gy < H && gx >= 0 && gx < W;
         uint8_t* dst = exp_tile + (size_t)row * PSTRIDE;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * acc_cols + mb * CW);
-        uint32_t r[CW / 16][16];
 #pragma unroll
-        for (int c16 = 0; c16 < CW / 16; ++c16) ptx::tmem_ld_32x32b_x16(taddr + c16 * 16, r[c16]);
-        ptx::tmem_ld_wait();
-        if (mb + (nd >> 2) >= g.MB) {                    // this warp's last TMEM read of the tile: hand it back
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&t_empty[s]);
-        }
-        if (row < g.n_pix) {
+        for (int c16 = 0; c16 < CW / 16; ++c16) {
 #pragma unroll
-          for (int c16 = 0; c16 < CW / 16; ++c16) {
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(hsh_exp + c16 * 16 + h8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(hsh_exp + c16 * 16 + h8 * 8 + 4);
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
+            uint32_t o[4];
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              const float4 b0 = *reinterpret_cast<const float4*>(hsh_exp + c16 * 16 + h8 * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(hsh_exp + c16 * 16 + h8 * 8 + 4);
-              const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
-                                    make_float2(b1.z, b1.w)};
-              uint32_t o[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 v = silu2(make_float2(__uint_as_float(r[c16][h8 * 8 + 2 * i]), __uint_as_float(r[c16][h8 * 8 + 2 * i + 1])), bb[i]);
-                o[i] = in_img ? pack_bf16x2(v.x, v.y) : 0u;
-              }
-              *reinterpret_cast<uint4*>(dst + c16 * 32 + h8 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            for (int i = 0; i < 4; ++i) {
+              const float2 v = silu2(make_float2(__uint_as_float(r[c16][h8 * 8 + 2 * i]), __uint_as_float(r[c16][h8 * 8 + 2 * i + 1])), bb[i]);
+              o[i] = in_img ? pack_bf16x2(v.x, v.y) : 0u;
             }
+            *reinterpret_cast<uint4*>(dst + c16 * 32 + h8 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
           }
+        }
+      };
+      if constexpr (CW <= 48) {
+        uint32_t ra[CW / 16][16], rb[CW / 16][16];
+        int mb = half;
+        if (mb < g.MB) ld_block(ra, mb);
+        while (mb < g.MB) {
+          const int mb2 = mb + mstep;
+          ptx::tmem_ld_wait();                             // ra landed
+          if (mb2 < g.MB) ld_block(rb, mb2); else release_tmem();
+          swish_block(ra, mb);
+          if (mb2 >= g.MB) break;
+          const int mb3 = mb2 + mstep;
+          ptx::tmem_ld_wait();                             // rb landed
+          if (mb3 < g.MB) ld_block(ra, mb3); else release_tmem();
+          swish_block(rb, mb2);
+          mb = mb3;
+        }
+      } else {                                             // 64-channel chunks: two buffers would not fit the registers
+        uint32_t ra[CW / 16][16];
+        for (int mb = half; mb < g.MB; mb += mstep) {
+          ld_block(ra, mb);
+          ptx::tmem_ld_wait();
+          if (mb + mstep >= g.MB) release_tmem();
+          swish_block(ra, mb);
         }
       }
       if (half >= g.MB) {                                // (no block for this warp in a one-block tile)
