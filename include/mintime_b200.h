@@ -24,9 +24,10 @@
 extern "C" {
 #endif
 
-#define MT_ABI_VERSION 4   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
+#define MT_ABI_VERSION 5   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
                             * 3: + the backward entry points of the transformer (mt_*_bwd, mt_grad_prep, mt_geglu_*)
-                            * 4: mt_clip_meta_fwd mask_padding semantics; fused divided attention; extractor training */
+                            * 4: mt_clip_meta_fwd mask_padding semantics; fused divided attention; extractor training
+                            * 5: + mt_linear_wgrad_nt (weight gradient from row-major operands) */
 
 enum { MT_PREC_FP32 = 0, MT_PREC_BF16 = 1 };
 enum { MT_OK = 0, MT_ERR_ARG = -1, MT_ERR_WORKSPACE = -2, MT_ERR_UNSUPPORTED = -3, MT_ERR_DRIVER = -4 };
@@ -318,6 +319,12 @@ int mt_grad_prep(int precision, const void* src, int src_is_f32, void* out_rm, v
  * output tile split over the SMs (partial tiles are summed by the TMA reduce-add of the epilogue, so the summation order
  * of the fp32 partials is not fixed). */
 int mt_linear_wgrad(int precision, const void* dy_t, const void* x_t, float* dw, int n_out, int k_in, int mp, void* stream);
+
+/* The same weight gradient straight from the row-major operands: dw f32 [n_out][k_in] += dy [m][n_out]^T * x [m][k_in]
+ * (bf16 only; n_out, k_in multiples of 64; any m).  Both operands enter tcgen05.mma MN-major (the contraction index is
+ * the slow one in memory), so no transposed copies (mt_grad_prep out_t) are needed: the backward of
+ * size_invariant_timesformer.py:109-144 / :65-76 w.r.t. to_qkv / to_out / net.0 / net.3 weights. */
+int mt_linear_wgrad_nt(int precision, const void* dy, const void* x, float* dw, int n_out, int k_in, int m, void* stream);
 
 /* out[c] (+)= sum_r in[r][c], fixed summation order. */
 int mt_colsum_f32(const float* in, float* out, int rows, int cols, int accumulate, void* stream);

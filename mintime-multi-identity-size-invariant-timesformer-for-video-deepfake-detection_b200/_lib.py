@@ -24,7 +24,7 @@ EXPORTS = [
     "mt_fused_attn_workspace_bytes", "mt_fused_attn_fwd", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
     "mt_dwconv_chunks", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
     "mt_aggregate_attn_fwd", "mt_clip_meta_fwd",
-    "mt_grad_prep_workspace_bytes", "mt_grad_prep", "mt_linear_wgrad", "mt_colsum_f32", "mt_layernorm_bwd_workspace_bytes", "mt_layernorm_bwd",
+    "mt_grad_prep_workspace_bytes", "mt_grad_prep", "mt_linear_wgrad", "mt_linear_wgrad_nt", "mt_colsum_f32", "mt_layernorm_bwd_workspace_bytes", "mt_layernorm_bwd",
     "mt_geglu_fwd", "mt_geglu_bwd", "mt_divided_attn_bwd_workspace_bytes", "mt_divided_attn_bwd", "mt_embed_bwd",
     "mt_head_bwd_workspace_bytes", "mt_head_bwd",
     "mt_extractor_train_workspace_bytes", "mt_bn_stats", "mt_bn_act_fwd", "mt_bn_act_bwd", "mt_stem_raw_fwd", "mt_stem_wgrad",
@@ -133,6 +133,7 @@ def load() -> C.CDLL:
     lib.mt_grad_prep.argtypes = [i32, vp, i32, vp, vp, fp, i32, i32, i32, i32, vp, sz, vp]
     lib.mt_colsum_f32.argtypes = [fp, fp, i32, i32, i32, vp]
     lib.mt_linear_wgrad.argtypes = [i32, vp, vp, fp, i32, i32, i32, vp]
+    lib.mt_linear_wgrad_nt.argtypes = [i32, vp, vp, fp, i32, i32, i32, vp]
     lib.mt_layernorm_bwd_workspace_bytes.argtypes = [i32, i32]
     lib.mt_layernorm_bwd_workspace_bytes.restype = sz
     lib.mt_layernorm_bwd.argtypes = [i32, fp, fp, vp, fp, fp, i32, i32, vp, sz, vp]
@@ -173,11 +174,11 @@ def load() -> C.CDLL:
     lib.mt_prof_launch_count.restype = C.c_ulonglong
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name.endswith(("_fwd", "_bwd")) or name in ("mt_grad_prep", "mt_colsum_f32", "mt_linear_wgrad", "mt_bn_stats",
+        if name.endswith(("_fwd", "_bwd")) or name in ("mt_grad_prep", "mt_colsum_f32", "mt_linear_wgrad", "mt_linear_wgrad_nt", "mt_bn_stats",
                                                        "mt_stem_wgrad", "mt_dwconv_dgrad", "mt_dwconv_wgrad", "mt_group_mean",
                                                        "mt_gate_mul", "mt_scale_add", "mt_conv1x1_wgrad"):
             fn.restype = i32
-    if lib.mt_abi_version() != 4:
+    if lib.mt_abi_version() != 5:
         raise RuntimeError("mintime_b200: ABI version mismatch between _lib.py and libmintime_b200.so")
     _lib = lib
     return lib

@@ -144,6 +144,7 @@ struct GemmArgs {
   int rows_per_gate;
   EpiParams epi;
   int splits;         // > 1: split-K request (honoured for EPI_RESID_F32 without bias on the tensor-core path)
+  int mn_major;       // 1: a is T [K][M] and w is T [K][N] (contraction index slow): dW = dY^T X without transposed copies
 };
 
 // One group of 8 consecutive output columns [col, col+8) of row `row` (both already bounds-checked).

@@ -44,6 +44,7 @@ struct TcParams {
   int acc_stages;   // TMEM accumulator buffers (2, or 1 when two CTAs share the SM's 512 columns at block_n > 128)
   int gate_imgs;    // > 0: SE gate rows of up to this many images are staged in smem per tile (GATED)
   int b_resident;   // 1: the block's weight slice (one column tile, all k-blocks) is loaded into smem once per block
+  int mn_major;     // 1: both operands MN-major (64-wide atoms, see ptx::umma_smem_desc_mn_sw128)
   int n_outer;      // 1: 2-D grid, blockIdx.y = the block's (fixed) column tile, blockIdx.x strides over the row tiles
   int splits;       // split-K (EPI_RESID_F32 through the TMA reduce-add only): every output tile is worked on by
   int kb_per_split; // `splits` tiles, each over kb_per_split k-blocks; the cp.reduce .add epilogue sums them in L2
@@ -257,9 +258,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
-          ptx::tma_load_2d(smem_a + ps.stage * kAStageBytes, &tmap_a, &full_bar[ps.stage], kb * kBlockK, m0);
-          if (!p.b_resident)
-            ptx::tma_load_2d(smem_b + ps.stage * b_stage_bytes, &tmap_b, &full_bar[ps.stage], kb * kBlockK, n0);
+          if (p.mn_major) {
+            // 64-channel atoms (8 KiB: 64 tokens x 128 bytes) side by side; rows beyond K / columns beyond M, N zero-fill
+            for (int j = 0; j < kBlockM / 64; ++j)
+              ptx::tma_load_2d(smem_a + ps.stage * kAStageBytes + j * 8192, &tmap_a, &full_bar[ps.stage], m0 + j * 64,
+                               kb * kBlockK);
+            for (int j = 0; j < p.block_n / 64; ++j)
+              ptx::tma_load_2d(smem_b + ps.stage * b_stage_bytes + j * 8192, &tmap_b, &full_bar[ps.stage], n0 + j * 64,
+                               kb * kBlockK);
+          } else {
+            ptx::tma_load_2d(smem_a + ps.stage * kAStageBytes, &tmap_a, &full_bar[ps.stage], kb * kBlockK, m0);
+            if (!p.b_resident)
+              ptx::tma_load_2d(smem_b + ps.stage * b_stage_bytes, &tmap_b, &full_bar[ps.stage], kb * kBlockK, n0);
+          }
           ps.advance(p.stages);
         }
       }
@@ -269,7 +280,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================================================== MMA issuer
     if (lane == 0) {
       PipeState ps;
-      const uint32_t idesc = ptx::umma_idesc_bf16_f32(kBlockM, (uint32_t)p.block_n);
+      const uint32_t idesc = p.mn_major ? ptx::umma_idesc_bf16_f32_mn(kBlockM, (uint32_t)p.block_n)
+                                        : ptx::umma_idesc_bf16_f32(kBlockM, (uint32_t)p.block_n);
       if (p.b_resident) ptx::mbar_wait(b_full, 0);
       int it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
@@ -287,8 +299,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int k_left = p.K - kb * kBlockK;
           const int ksteps = k_left >= kBlockK ? 4 : (k_left + 15) / 16;  // TMA zero-filled the K tail
           for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = ptx::umma_smem_desc_sw128(a_addr + k * 32);
-            const uint64_t bdesc = ptx::umma_smem_desc_sw128(b_addr + k * 32);
+            const uint64_t adesc = p.mn_major ? ptx::umma_smem_desc_mn_sw128(a_addr + k * 2048, 8192)
+                                              : ptx::umma_smem_desc_sw128(a_addr + k * 32);
+            const uint64_t bdesc = p.mn_major ? ptx::umma_smem_desc_mn_sw128(b_addr + k * 2048, 8192)
+                                              : ptx::umma_smem_desc_sw128(b_addr + k * 32);
             ptx::umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[ps.stage]);  // smem slot free once these MMAs retire
@@ -781,7 +795,12 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   constexpr int kEW = epi_warps<KIND, TMA_OUT>();
   const int num_kb = (g.K + kBlockK - 1) / kBlockK;
   const int b_block = bn * kBlockK * 2;
-  p.b_resident = (p.tiles_n == 1 && num_kb * b_block <= 40 * 1024) ? 1 : 0;
+  p.mn_major = g.mn_major;
+  if (g.mn_major && (bn % 64 != 0 || GATED)) {
+    set_error("gemm_tc: MN-major operands need 64-column tiles (N = %d) and no SE gate", g.N);
+    return MT_ERR_ARG;
+  }
+  p.b_resident = (!g.mn_major && p.tiles_n == 1 && num_kb * b_block <= 40 * 1024) ? 1 : 0;
   p.n_outer = 0;
   // Wide layers with several k-blocks run one block per SM (below) and were bound by re-streaming the weight slice
   // for every 128-row tile (L2 -> SM: e.g. N=1152 K=192 moves 98 KB of W next to 49 KB of A per tile).  Give each
@@ -832,9 +851,9 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
   const size_t smem = (size_t)stages * stage_bytes + fixed;
 
   CUtensorMap ta, tb, tout;
-  int rc = make_tmap_2d(&ta, g.a, false, g.M, g.K, g.K, kBlockM);
+  int rc = g.mn_major ? make_tmap_2d(&ta, g.a, false, g.K, g.M, g.M, 64) : make_tmap_2d(&ta, g.a, false, g.M, g.K, g.K, kBlockM);
   if (rc) return rc;
-  rc = make_tmap_2d(&tb, g.w, false, g.N, g.K, g.K, bn);
+  rc = g.mn_major ? make_tmap_2d(&tb, g.w, false, g.K, g.N, g.N, 64) : make_tmap_2d(&tb, g.w, false, g.N, g.K, g.K, bn);
   if (rc) return rc;
   if (TMA_OUT) {
     const bool f32 = KIND == EPI_RESID_F32;
@@ -883,7 +902,7 @@ template <int KIND, bool GATED>
 int launch_tc(const GemmArgs& g, cudaStream_t stream) {
   if constexpr (!GATED && (KIND == EPI_STORE || KIND == EPI_GEGLU || KIND == EPI_RESID_F32)) {
     // large transformer contractions: CTA-pair kernel (256x256 tiles, cta_group::2)
-    if (tc2_enabled() && g.splits <= 1 && tc2_eligible(g)) {
+    if (tc2_enabled() && g.splits <= 1 && !g.mn_major && tc2_eligible(g)) {
       if constexpr (KIND != EPI_RESID_F32) {
         if (tc2a_enabled() && tc2a_eligible(g)) return launch_tc2a<KIND, (KIND == EPI_GEGLU ? 8 : 4)>(g, stream);
       }
@@ -1014,10 +1033,12 @@ int make_tmap_nhwc_bf16_plain(CUtensorMap_st* m, const void* base, int n, int h,
 
 int launch_gemm(int precision, const GemmArgs& g, cudaStream_t stream) {
   MT_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  MT_REQUIRE(g.N % 8 == 0 && g.K % 8 == 0, "gemm: N (%d) and K (%d) must be multiples of 8", g.N, g.K);
+  MT_REQUIRE(g.N % 8 == 0 && (g.K % 8 == 0 || g.mn_major), "gemm: N (%d) and K (%d) must be multiples of 8", g.N, g.K);
   MT_REQUIRE(g.a && g.w && g.epi.out, "gemm: null operand");
   const bool gated = g.gate != nullptr;
   MT_REQUIRE(!gated || g.rows_per_gate > 0, "gemm: rows_per_gate must be > 0 with a gate");
+  MT_REQUIRE(!g.mn_major || (precision == MT_PREC_BF16 && g.epi.kind == EPI_RESID_F32 && g.M % 8 == 0),
+             "gemm: MN-major operands are a bf16 tensor-core path of the fp32-accumulate epilogue only");
   static const char* kKind[] = {"store", "resid", "geglu", "embed"};
   const double es = precision == MT_PREC_FP32 ? 4.0 : 2.0;
   const double mn = (double)g.M * g.N;

@@ -162,10 +162,27 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major operand (the contraction index is the SLOW index in memory, e.g. dY [tokens][channels] as the A operand
+// of dW = dY^T X): TMA boxes of 64 channels (128 bytes, SWIZZLE_128B) x 64 tokens; canonical layout in 16-byte units
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) -- 8-token groups 1024 bytes apart (SBO), 64-channel atoms `atom_stride` bytes apart
+// (LBO).  One K = 16 MMA spans two 8-token groups; the next one starts 2048 bytes further.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t atom_stride) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((atom_stride >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: D = f32 (bits [4,6) = 1), A = B = bf16 (bits [7,10) = [10,13) = 1),
 // both K-major (bits 15, 16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 __device__ __forceinline__ uint32_t umma_idesc_bf16_f32(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// the same with both operands MN-major (bits 15, 16 = 1)
+__device__ __forceinline__ uint32_t umma_idesc_bf16_f32_mn(uint32_t m, uint32_t n) {
+  return umma_idesc_bf16_f32(m, n) | (1u << 15) | (1u << 16);
 }
 
 }  // namespace ptx

@@ -729,6 +729,20 @@ extern "C" int mt_linear_wgrad(int precision, const void* dy_t, const void* x_t,
   return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mt_linear_wgrad_nt(int precision, const void* dy, const void* x, float* dw, int n_out, int k_in, int m,
+                                  void* stream) {
+  MT_REQUIRE(dy && x && dw && n_out > 0 && k_in > 0 && m > 0, "linear_wgrad_nt: bad argument");
+  MT_REQUIRE(precision == MT_PREC_BF16 && n_out % 64 == 0 && k_in % 64 == 0,
+             "linear_wgrad_nt: bf16 only, n_out (%d) and k_in (%d) multiples of 64", n_out, k_in);
+  GemmArgs g{};
+  g.a = dy; g.w = x; g.M = n_out; g.N = k_in; g.K = m;
+  g.mn_major = 1;
+  g.epi.kind = EPI_RESID_F32; g.epi.M = n_out; g.epi.N = k_in; g.epi.bias = nullptr; g.epi.out = dw; g.epi.ldo = k_in;
+  const int tiles = ((n_out + 127) / 128) * ((k_in + 255) / 256);
+  g.splits = std::max(1, (sm_count() + tiles / 2) / tiles);
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mt_colsum_f32(const float* in, float* out, int rows, int cols, int accumulate, void* stream) {
   MT_REQUIRE(in && out && rows > 0 && cols > 0, "colsum: bad argument");
   return launch_colsum(in, out, rows, cols, accumulate, reinterpret_cast<cudaStream_t>(stream));

@@ -371,3 +371,19 @@ def linear_wgrad_(dw, dy_t, x_t, precision="bf16"):
                                          mp, _lib.stream_ptr())
     _lib.check(rc, "mt_linear_wgrad")
     return dw
+
+
+def linear_wgrad_nt_(dw, dy, x):
+    """dw (float32 [n_out, k_in], in place) += dy [m, n_out].T @ x [m, k_in], bf16 row-major operands as they are
+    (MN-major tcgen05 operands: no transposed copies); n_out and k_in multiples of 64"""
+    _prep(dy, torch.bfloat16); _prep(x, torch.bfloat16); _prep(dw, torch.float32)
+    m, n_out = dy.shape
+    k_in = x.shape[1]
+    if x.shape[0] != m or tuple(dw.shape) != (n_out, k_in):
+        raise ValueError("linear_wgrad_nt_: shape mismatch")
+    _lib.require_device(dw.device)
+    with torch.cuda.device(dw.device):
+        rc = _lib.load().mt_linear_wgrad_nt(_lib.prec_id("bf16"), dy.data_ptr(), x.data_ptr(), dw.data_ptr(), n_out, k_in, m,
+                                            _lib.stream_ptr())
+    _lib.check(rc, "mt_linear_wgrad_nt")
+    return dw

@@ -73,6 +73,21 @@ def test_linear_wgrad_split_k(prec, n_out, k_in, m):
     assert rel_err(dw, ref) <= _tol(prec, 1e-5, 1e-5)        # bf16 operands are exact products, fp32 accumulation
 
 
+@pytest.mark.parametrize("n_out,k_in,m", [(512, 512, 785 * 3), (1536, 512, 4000), (4096, 512, 1570), (512, 2048, 25120),
+                                          (128, 64, 100), (192, 320, 777)])
+def test_linear_wgrad_from_row_major_operands(n_out, k_in, m):
+    """dW += dY^T X with dY [m][n_out] and X [m][k_in] as they lie in memory (MN-major tcgen05 operands, TMA zero fill for
+    the ragged token tail): equals the transposed-copy route and the fp64 product."""
+    g = torch.Generator().manual_seed(n_out + k_in + m)
+    dy = torch.randn((m, n_out), generator=g).to(DEV).bfloat16()
+    x = torch.randn((m, k_in), generator=g).to(DEV).bfloat16()
+    dw0 = torch.randn((n_out, k_in), generator=g).to(DEV)
+    dw = dw0.clone()
+    ops.linear_wgrad_nt_(dw, dy, x)
+    ref = dw0.double() + dy.double().t() @ x.double()
+    assert rel_err(dw, ref) <= 1e-5
+
+
 # --------------------------------------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("rows,dim", [(785 * 2, 512), (37, 128), (5000, 1024)])

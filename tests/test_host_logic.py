@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.mt_abi_version.restype = ctypes.c_int
-    assert lib.mt_abi_version() == 4
+    assert lib.mt_abi_version() == 5
     lib.mt_last_error.restype = ctypes.c_char_p
     assert lib.mt_last_error() == b""
 
