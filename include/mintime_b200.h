@@ -27,7 +27,7 @@ extern "C" {
 #define MT_ABI_VERSION 5   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
                             * 3: + the backward entry points of the transformer (mt_*_bwd, mt_grad_prep, mt_geglu_*)
                             * 4: mt_clip_meta_fwd mask_padding semantics; fused divided attention; extractor training
-                            * 5: + mt_linear_wgrad_nt (weight gradient from row-major operands) */
+                            * 5: + mt_linear_wgrad_nt (weight gradient from row-major operands), mt_geglu_bwd_colsum */
 
 enum { MT_PREC_FP32 = 0, MT_PREC_BF16 = 1 };
 enum { MT_OK = 0, MT_ERR_ARG = -1, MT_ERR_WORKSPACE = -2, MT_ERR_UNSUPPORTED = -3, MT_ERR_DRIVER = -4 };
@@ -340,6 +340,11 @@ int mt_layernorm_bwd(int precision, const float* x, const float* gamma, const vo
  * (The training forward keeps h; inference uses the fused mt_linear_geglu_fwd.) */
 int mt_geglu_fwd(int precision, const void* h, void* out, int m, int n_out, void* stream);
 int mt_geglu_bwd(int precision, const void* h, const void* dout, void* dh, int m, int n_out, void* stream);
+/* mt_geglu_bwd that also returns colsum f32 [2*n_out] = the column sums of dh (= d loss / d net.0.bias, interleaved
+ * order), summed in a fixed order; workspace: mt_geglu_bwd_colsum_workspace_bytes(m, n_out) bytes. */
+size_t mt_geglu_bwd_colsum_workspace_bytes(int m, int n_out);
+int mt_geglu_bwd_colsum(int precision, const void* h, const void* dout, void* dh, float* colsum, int m, int n_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of mt_divided_attn_fwd: qkv, mask, identities_mask as in the forward (probabilities are recomputed),
  * dout T [B][1+f*n][heads*dim_head] -> dqkv T [B][1+f*n][3*heads*dim_head] (every element written). */

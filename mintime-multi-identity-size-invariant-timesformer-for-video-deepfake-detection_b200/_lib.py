@@ -25,7 +25,7 @@ EXPORTS = [
     "mt_dwconv_chunks", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
     "mt_aggregate_attn_fwd", "mt_clip_meta_fwd",
     "mt_grad_prep_workspace_bytes", "mt_grad_prep", "mt_linear_wgrad", "mt_linear_wgrad_nt", "mt_colsum_f32", "mt_layernorm_bwd_workspace_bytes", "mt_layernorm_bwd",
-    "mt_geglu_fwd", "mt_geglu_bwd", "mt_divided_attn_bwd_workspace_bytes", "mt_divided_attn_bwd", "mt_embed_bwd",
+    "mt_geglu_fwd", "mt_geglu_bwd", "mt_geglu_bwd_colsum_workspace_bytes", "mt_geglu_bwd_colsum", "mt_divided_attn_bwd_workspace_bytes", "mt_divided_attn_bwd", "mt_embed_bwd",
     "mt_head_bwd_workspace_bytes", "mt_head_bwd",
     "mt_extractor_train_workspace_bytes", "mt_bn_stats", "mt_bn_act_fwd", "mt_bn_act_bwd", "mt_stem_raw_fwd", "mt_stem_wgrad",
     "mt_dwconv_raw_fwd", "mt_dwconv_dgrad", "mt_dwconv_wgrad", "mt_group_mean", "mt_se_fc_fwd", "mt_se_fc_bwd", "mt_gate_mul",
@@ -139,6 +139,10 @@ def load() -> C.CDLL:
     lib.mt_layernorm_bwd.argtypes = [i32, fp, fp, vp, fp, fp, i32, i32, vp, sz, vp]
     lib.mt_geglu_fwd.argtypes = [i32, vp, vp, i32, i32, vp]
     lib.mt_geglu_bwd.argtypes = [i32, vp, vp, vp, i32, i32, vp]
+    lib.mt_geglu_bwd_colsum_workspace_bytes.argtypes = [i32, i32]
+    lib.mt_geglu_bwd_colsum_workspace_bytes.restype = C.c_size_t
+    lib.mt_geglu_bwd_colsum.argtypes = [i32, vp, vp, vp, fp, i32, i32, vp, C.c_size_t, vp]
+    lib.mt_geglu_bwd_colsum.restype = i32
     lib.mt_divided_attn_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.mt_divided_attn_bwd_workspace_bytes.restype = sz
     lib.mt_divided_attn_bwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, sz, vp]

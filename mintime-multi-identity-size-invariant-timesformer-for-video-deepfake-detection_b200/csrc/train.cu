@@ -299,6 +299,44 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const T* __restrict__ h,
   store8(dh + row * 2 * hd + hc + 32, g);
 }
 
+// The same with the bias gradient of net.0 folded in: a block walks rows blockIdx.x, + gridDim.x, ... with one thread
+// per 8-column group and keeps the column sums of (du | dg) in registers; part[block][2*hd] are summed over the blocks
+// in a fixed order by colsum_kernel (deterministic).  Saves the separate pass over dh (205 MB at B = 32).
+template <typename T>
+__global__ void __launch_bounds__(256) geglu_bwd_colsum_kernel(const T* __restrict__ h, const T* __restrict__ dout,
+                                                               T* __restrict__ dh, float* __restrict__ part, int rows,
+                                                               int hd) {
+  const int cg = blockIdx.y * 256 + threadIdx.x;
+  if (cg >= (hd >> 3)) return;
+  const int oc = cg * 8;
+  const int hc = (oc >> 5) * 64 + (oc & 31);
+  float su[8], sg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { su[i] = 0.f; sg[i] = 0.f; }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    float u[8], g[8], d[8];
+    load8(h + (size_t)row * 2 * hd + hc, u);
+    load8(h + (size_t)row * 2 * hd + hc + 32, g);
+    load8(dout + (size_t)row * hd + oc, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float cdf = 0.5f * (1.0f + erff(g[i] * 0.70710678118654752f));
+      const float pdf = 0.39894228040143268f * expf(-0.5f * g[i] * g[i]);
+      const float du = d[i] * g[i] * cdf;
+      const float dg = d[i] * u[i] * fmaf(g[i], pdf, cdf);
+      u[i] = du;
+      g[i] = dg;
+      su[i] += du;
+      sg[i] += dg;
+    }
+    store8(dh + (size_t)row * 2 * hd + hc, u);
+    store8(dh + (size_t)row * 2 * hd + hc + 32, g);
+  }
+  float* p = part + (size_t)blockIdx.x * 2 * hd + hc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { p[i] = su[i]; p[32 + i] = sg[i]; }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Attention core backward (Attention.forward :114-141, attn :80-87), probabilities recomputed from qkv.
 // Workspace (fp32):  ws_kv [B*heads][N][128]  CLS-row contribution to dK (0..63) and dV (64..127) of every key
@@ -849,6 +887,38 @@ extern "C" int mt_geglu_bwd(int precision, const void* h, const void* dout, void
   else { set_error("geglu_bwd: unknown precision %d", precision); return MT_ERR_ARG; }
   MT_LAUNCH_CHECK("geglu_bwd_kernel");
   return MT_OK;
+}
+
+static int geglu_colsum_grid(int m) { return std::min(m, 4 * sm_count()); }
+
+extern "C" size_t mt_geglu_bwd_colsum_workspace_bytes(int m, int n_out) {
+  if (m <= 0 || n_out <= 0) return 0;
+  return (size_t)geglu_colsum_grid(m) * 2 * (size_t)n_out * sizeof(float);
+}
+
+extern "C" int mt_geglu_bwd_colsum(int precision, const void* h, const void* dout, void* dh, float* colsum, int m, int n_out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  MT_REQUIRE(h && dout && dh && colsum && m > 0 && n_out > 0 && n_out % 32 == 0, "geglu_bwd_colsum: bad argument (n_out %% 32)");
+  if (!workspace || workspace_bytes < mt_geglu_bwd_colsum_workspace_bytes(m, n_out)) {
+    set_error("geglu_bwd_colsum: workspace too small");
+    return MT_ERR_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid(geglu_colsum_grid(m), (n_out / 8 + 255) / 256);
+  float* part = reinterpret_cast<float*>(workspace);
+  const size_t es = precision == MT_PREC_FP32 ? 4 : 2;
+  {
+    ProfScope prof(st, 24.0 * m * n_out, (double)m * n_out * 5 * es, "geglu_bwd");
+    if (precision == MT_PREC_FP32)
+      geglu_bwd_colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(h), reinterpret_cast<const float*>(dout),
+                                                           reinterpret_cast<float*>(dh), part, m, n_out);
+    else if (precision == MT_PREC_BF16)
+      geglu_bwd_colsum_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(h), reinterpret_cast<const bf16*>(dout),
+                                                          reinterpret_cast<bf16*>(dh), part, m, n_out);
+    else { set_error("geglu_bwd_colsum: unknown precision %d", precision); return MT_ERR_ARG; }
+    MT_LAUNCH_CHECK("geglu_bwd_colsum_kernel");
+  }
+  return launch_colsum(part, colsum, (int)grid.x, 2 * n_out, 0, st);
 }
 
 extern "C" size_t mt_divided_attn_bwd_workspace_bytes(int batch, int f, int n, int heads) {

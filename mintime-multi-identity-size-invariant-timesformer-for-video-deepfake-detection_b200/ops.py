@@ -300,6 +300,23 @@ def geglu_bwd(h, dout, precision="bf16"):
     return dh
 
 
+def geglu_bwd_colsum(h, dout, precision="bf16"):
+    """(dh, column sums of dh as float32 [2*n_out]) in one pass -- the data and the bias gradient of net.0"""
+    T = _T(precision)
+    _prep(h, T); _prep(dout, T)
+    m, n2 = h.shape
+    _lib.require_device(h.device)
+    lib = _lib.load()
+    dh = torch.empty_like(h)
+    cs = torch.empty((n2,), dtype=torch.float32, device=h.device)
+    ws = torch.empty((lib.mt_geglu_bwd_colsum_workspace_bytes(m, n2 // 2),), dtype=torch.uint8, device=h.device)
+    with torch.cuda.device(h.device):
+        rc = lib.mt_geglu_bwd_colsum(_lib.prec_id(precision), h.data_ptr(), dout.data_ptr(), dh.data_ptr(), cs.data_ptr(), m,
+                                     n2 // 2, ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "mt_geglu_bwd_colsum")
+    return dh, cs
+
+
 def divided_attention_bwd(qkv, dout, mask_u8, idmask_u8, mode: str, f: int, n: int, heads: int, dim_head: int = 64,
                           precision="bf16"):
     """Backward of divided_attention: (qkv, d out) -> d qkv, same shape as qkv."""

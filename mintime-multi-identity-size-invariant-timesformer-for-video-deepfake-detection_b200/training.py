@@ -256,16 +256,23 @@ class TsfTrainFunction(torch.autograd.Function):
         side = [main] if getattr(model, "_serial_wgrad", False) else _side_streams(model, dev)
         turn = [0]
 
+        nt_ok = precision == "bf16" and not getattr(model, "_wgrad_transposed", False)   # (the flag keeps the old route: A/B runs)
+
         def wgrad(dst, dy, x, after=None, **dy_kw):
-            """dst += dy^T x on a side stream: both transposes (mt_grad_prep), the split-K GEMM and `after`."""
+            """dst += dy^T x on a side stream: the split-K GEMM (fp32 path / CLS-skipping operand: after both
+            transposes by mt_grad_prep) and `after`."""
             s_ = side[turn[0] % len(side)]
             turn[0] += 1
             if s_ is not main:
                 s_.wait_stream(main)
             with torch.cuda.stream(s_):
-                _, dyT, _ = ops.grad_prep(dy, want_t=True, precision=precision, **dy_kw)
-                _, xT, _ = ops.grad_prep(x, want_t=True, precision=precision)
-                ops.linear_wgrad_(dst, dyT, xT, precision)
+                if nt_ok and not dy_kw and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16:
+                    # bf16 path: the operands enter the tensor cores as they lie in memory (MN-major descriptors)
+                    ops.linear_wgrad_nt_(dst, dy, x)
+                else:
+                    _, dyT, _ = ops.grad_prep(dy, want_t=True, precision=precision, **dy_kw)
+                    _, xT, _ = ops.grad_prep(x, want_t=True, precision=precision)
+                    ops.linear_wgrad_(dst, dyT, xT, precision)
                 if after is not None:
                     after()
             if s_ is not main:
@@ -299,9 +306,8 @@ class TsfTrainFunction(torch.autograd.Function):
             G["2.fn.net.3.bias"].copy_(cs)
             dgo = ops.pointwise(gb, L["ff.w2_t"], precision=precision)
             wgrad(G["2.fn.net.3.weight"], gb, go)
-            dh_ = ops.geglu_bwd(h, dgo, precision)
+            dh_, cs = ops.geglu_bwd_colsum(h, dgo, precision)      # (+ the bias gradient of net.0 in the same pass)
             del dgo, gb
-            _, _, cs = ops.grad_prep(dh_, want_colsum=True, precision=precision)
             dw1 = torch.zeros((8 * dim, dim), dtype=f32, device=dev)      # interleaved row order of the packed weight
             wgrad(dw1, dh_, xn, after=lambda dw1=dw1, dst=G["2.fn.net.0.weight"]: dst.copy_(_uninterleave(dw1)))
             G["2.fn.net.0.bias"].copy_(_uninterleave(cs))

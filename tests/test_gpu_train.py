@@ -126,6 +126,11 @@ def test_geglu_fwd_bwd(prec):
     dh = _uninterleave(dh_int.t().contiguous()).t()
     assert rel_err(out, ref) <= _tol(prec, 1e-6, 3e-3)
     assert rel_err(dh, hr.grad) <= _tol(prec, 1e-6, 3e-3)
+    # the same backward with the bias gradient (column sums of dh) folded in
+    dh2, cs = ops.geglu_bwd_colsum(h_int, dout, prec)
+    torch.cuda.synchronize()
+    assert torch.equal(dh2, dh_int)
+    assert rel_err(_uninterleave(cs), hr.grad.sum(0)) <= _tol(prec, 1e-5, 3e-3)
 
 
 # --------------------------------------------------------------------------------------------- attention core
