@@ -27,7 +27,7 @@ extern "C" {
 #define MT_ABI_VERSION 5   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
                             * 3: + the backward entry points of the transformer (mt_*_bwd, mt_grad_prep, mt_geglu_*)
                             * 4: mt_clip_meta_fwd mask_padding semantics; fused divided attention; extractor training
-                            * 5: + mt_linear_wgrad_nt (weight gradient from row-major operands), mt_geglu_bwd_colsum */
+                            * 5: + mt_linear_wgrad_nt (weight gradient from row-major operands), mt_geglu_bwd_colsum, mt_xception_* */
 
 enum { MT_PREC_FP32 = 0, MT_PREC_BF16 = 1 };
 enum { MT_OK = 0, MT_ERR_ARG = -1, MT_ERR_WORKSPACE = -2, MT_ERR_UNSUPPORTED = -3, MT_ERR_DRIVER = -4 };
@@ -103,9 +103,36 @@ typedef struct {
   const float* out_w; const float* out_b;       /* f32 [num_classes][dim], [num_classes] */
 } mt_tsf_weights_t;
 
+/* Xception (models/xception.py:93-137), the alternative 2048-channel extractor (train.py:129-133):
+ *   conv1 / conv2      : dense 3x3 as im2col GEMMs: w T [cout][kp], column (ky*3+kx)*cin + ci, kp = 32 (27 padded) / 288,
+ *                        bn1 / bn2 folded
+ *   sep[34]            : the separable convolutions in forward order -- block1..block12 `rep` entries, conv3, conv4:
+ *                        dw_w f32 [9][cin] (SeparableConv2d.conv1, tap-major), pw = pointwise 1x1 with the following
+ *                        BatchNorm folded
+ *   skip[4]            : block1/2/3/12 `skip` 1x1 stride-2 projection with `skipbn` folded */
+typedef struct {
+  const float* dw_w;
+  mt_pw_t pw;
+} mt_xc_sep_t;
+
+typedef struct {
+  mt_pw_t conv1, conv2;
+  mt_xc_sep_t sep[34];
+  mt_pw_t skip[4];
+} mt_xception_weights_t;
+
 /* ---------------------------------------------------------------------------------------------
  * Whole-model entry points
  * ------------------------------------------------------------------------------------------- */
+
+/* Xception.forward == Xception.features (models/xception.py:146-184, :196-198), eval mode.
+ *   x      : frames NHWC [n_img][in_hw][in_hw][3], f32 or u8, as given to the module (no normalisation inside)
+ *   feats  : T [n_img * o * o][2048], o = mt_xception_out_hw(in_hw) (7 for 224): the reference's (n_img,2048,o,o) permuted
+ * Workspace: mt_xception_workspace_bytes(n_img, in_hw, precision), 1024-byte aligned. */
+int mt_xception_out_hw(int in_hw);
+size_t mt_xception_workspace_bytes(int n_img, int in_hw, int precision);
+int mt_xception_fwd(const mt_xception_weights_t* w, const void* x, int x_dtype, void* feats, int n_img, int in_hw,
+                    int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* EfficientNet.forward (models/efficientnet/efficientnet_pytorch/model.py:267-288), eval mode.
  *   x      : frames, NHWC [n_img][224][224][3], f32 (MT_IN_F32) or u8 (MT_IN_U8), raw 0..255

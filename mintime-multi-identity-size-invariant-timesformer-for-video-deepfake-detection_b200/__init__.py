@@ -9,7 +9,7 @@ or PyTorch fallback: calling a forward without the built library / without a GPU
 """
 from . import spec, synth  # noqa: F401  (pure-python, importable without the CUDA library)
 
-__all__ = ["spec", "synth", "EfficientNet", "SizeInvariantTimeSformer", "lib"]
+__all__ = ["spec", "synth", "EfficientNet", "Xception", "xception", "SizeInvariantTimeSformer", "lib"]
 
 
 def __getattr__(name):
@@ -17,6 +17,12 @@ def __getattr__(name):
     if name == "EfficientNet":
         from .efficientnet import EfficientNet
         return EfficientNet
+    if name == "Xception":
+        from .xception import Xception
+        return Xception
+    if name == "xception":
+        from .xception import xception
+        return xception
     if name == "SizeInvariantTimeSformer":
         from .size_invariant_timesformer import SizeInvariantTimeSformer
         return SizeInvariantTimeSformer

@@ -18,7 +18,7 @@ TSF_MAX_DEPTH = 16
 
 EXPORTS = [
     "mt_abi_version", "mt_last_error", "mt_device_check",
-    "mt_effnet_b0_workspace_bytes", "mt_effnet_b0_fwd", "mt_tsf_workspace_bytes", "mt_tsf_fwd",
+    "mt_effnet_b0_workspace_bytes", "mt_effnet_b0_fwd", "mt_xception_out_hw", "mt_xception_workspace_bytes", "mt_xception_fwd", "mt_tsf_workspace_bytes", "mt_tsf_fwd",
     "mt_pointwise_fwd", "mt_linear_residual_fwd", "mt_linear_geglu_fwd", "mt_patch_embed_fwd",
     "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_fused_attn_supported",
     "mt_fused_attn_workspace_bytes", "mt_fused_attn_fwd", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
@@ -46,6 +46,14 @@ class MBConv(C.Structure):
 
 class EffnetWeights(C.Structure):
     _fields_ = [("stem_w", fp), ("stem_shift", fp), ("blocks", MBConv * 16), ("head", PW)]
+
+
+class XcSep(C.Structure):
+    _fields_ = [("dw_w", fp), ("pw", PW)]
+
+
+class XceptionWeights(C.Structure):
+    _fields_ = [("conv1", PW), ("conv2", PW), ("sep", XcSep * 34), ("skip", PW * 4)]
 
 
 class AttnWeights(C.Structure):
@@ -95,6 +103,11 @@ def load() -> C.CDLL:
     lib.mt_effnet_b0_workspace_bytes.restype = sz
     lib.mt_effnet_b0_workspace_bytes.argtypes = [i32, i32]
     lib.mt_effnet_b0_fwd.argtypes = [C.POINTER(EffnetWeights), vp, i32, vp, i32, i32, vp, sz, vp]
+    lib.mt_xception_out_hw.argtypes = [i32]
+    lib.mt_xception_out_hw.restype = i32
+    lib.mt_xception_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.mt_xception_workspace_bytes.restype = sz
+    lib.mt_xception_fwd.argtypes = [C.POINTER(XceptionWeights), vp, i32, vp, i32, i32, i32, vp, sz, vp]
     lib.mt_tsf_workspace_bytes.restype = sz
     lib.mt_tsf_workspace_bytes.argtypes = [C.POINTER(TsfCfg), i32, i32]
     lib.mt_tsf_fwd.argtypes = [C.POINTER(TsfWeights), C.POINTER(TsfCfg), vp, vp, vp, vp, vp, vp, vp, vp, i32, i32,

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmintime_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "effnet.cu", "timesformer.cu", "fused_attn.cu", "train.cu", "effnet_train.cu"]
+SOURCES = ["api.cu", "gemm.cu", "effnet.cu", "timesformer.cu", "fused_attn.cu", "train.cu", "effnet_train.cu", "xception.cu"]
 
 
 def nvcc_path() -> str:

@@ -83,6 +83,44 @@ def make_effnet_state_dict(seed: int = 1234, conditioned: bool = False) -> Dict[
     return sd
 
 
+def make_xception_state_dict(seed: int = 2468, num_classes: int = 1) -> Dict[str, torch.Tensor]:
+    """Xception ``state_dict`` (names as in reference models/xception.py:93-137): He-normal convolutions, perturbed BatchNorm
+    statistics, conv1 scaled by 1/64 (raw 0..255 pixels), and -- like a trained residual network -- the last BatchNorm of every
+    block's main path damped (gamma ~ U(0.05, 0.15)) so that the twelve residual sums keep the activations O(1..20); bn4's
+    gamma is scaled by 0.1 so that the 2048 output features are O(1..10)."""
+    from .xception import XCEPTION_BLOCKS, sep_channels
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    sd["conv1.weight"] = _conv(rng, 32, 3, 3, scale=1.0 / 64.0)
+    _bn(rng, 32, "bn1", sd)
+    sd["conv2.weight"] = _conv(rng, 64, 32, 3)
+    _bn(rng, 64, "bn2", sd)
+
+    def sep(prefix, bn_prefix, cin, cout, damp=False):
+        sd[prefix + ".conv1.weight"] = _conv(rng, cin, 1, 3)
+        sd[prefix + ".pointwise.weight"] = _conv(rng, cout, cin, 1)
+        _bn(rng, cout, bn_prefix, sd)
+        if damp:
+            sd[bn_prefix + ".weight"] = torch.from_numpy(rng.uniform(0.05, 0.15, cout).astype(np.float32))
+
+    for bi, (cin, cout, reps, stride, relu0, grow_first) in enumerate(XCEPTION_BLOCKS):
+        p = f"block{bi + 1}."
+        if cout != cin or stride != 1:
+            sd[p + "skip.weight"] = _conv(rng, cout, cin, 1)
+            _bn(rng, cout, p + "skipbn", sd)
+        idx = 1 if relu0 else 0
+        chans = sep_channels(cin, cout, reps, grow_first)
+        for j, (a, b) in enumerate(chans):
+            sep(f"{p}rep.{idx}", f"{p}rep.{idx + 1}", a, b, damp=(j == len(chans) - 1))
+            idx += 3
+    sep("conv3", "bn3", 1024, 1536)
+    sep("conv4", "bn4", 1536, 2048)
+    sd["bn4.weight"] = sd["bn4.weight"] * 0.1
+    sd["fc.weight"] = torch.from_numpy((rng.standard_normal((num_classes, 2048)) * 0.01).astype(np.float32))
+    sd["fc.bias"] = torch.zeros(num_classes)
+    return sd
+
+
 def _trunc_normal(rng: np.random.Generator, shape, std: float = 0.02) -> torch.Tensor:
     # reference size_invariant_timesformer.py:200-214 uses trunc_normal_(std=.02) (cut at +-2, i.e.
     # 100 sigma: effectively a plain normal).

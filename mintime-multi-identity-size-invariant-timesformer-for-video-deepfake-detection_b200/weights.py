@@ -23,10 +23,10 @@ def _strip(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return sd
 
 
-def _bn_fold(sd, prefix: str) -> Tuple[torch.Tensor, torch.Tensor]:
+def _bn_fold(sd, prefix: str, eps: float = BN_EPS) -> Tuple[torch.Tensor, torch.Tensor]:
     g, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
     m, v = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
-    scale = g / torch.sqrt(v + BN_EPS)
+    scale = g / torch.sqrt(v + eps)
     return scale, b - m * scale
 
 
@@ -81,6 +81,59 @@ def pack_effnet(sd: Dict[str, torch.Tensor], precision: str, device) -> Packed:
         blk.se_expand_b = pk.p(sd[p + "_se_expand.bias"], f32, device)
         blk.project = pw(p + "_project_conv.weight", p + "_bn2")
     W.head = pw("_conv_head.weight", "_bn1")
+    pk.struct = W
+    return pk
+
+
+XC_BN_EPS = 1e-5          # nn.BatchNorm2d default: models/xception.py:91 sets BN = nn.BatchNorm2d with no eps argument
+
+
+def pack_xception(sd: Dict[str, torch.Tensor], precision: str, device) -> Packed:
+    """Xception ``state_dict`` (models/xception.py:93-137) -> mt_xception_weights_t: every BatchNorm folded into the 1x1 / dense
+    convolution in front of it, dense 3x3 filters as im2col rows ((ky,kx,ci) columns, conv1 padded 27 -> 32), depthwise
+    filters tap-major."""
+    from .xception import XCEPTION_BLOCKS, sep_channels
+    sd = {k: v.detach().cpu() for k, v in _strip(sd).items()}
+    T = _lib.torch_dtype(precision)
+    f32 = torch.float32
+    pk = Packed()
+    W = _lib.XceptionWeights()
+
+    def fold(w2d: torch.Tensor, bn_prefix: str) -> _lib.PW:
+        scale, shift = _bn_fold(sd, bn_prefix, XC_BN_EPS)
+        s = _lib.PW()
+        s.w = pk.p(w2d.double() * scale[:, None], T, device)
+        s.shift = pk.p(shift, f32, device)
+        return s
+
+    def dense3x3(key: str, bn_prefix: str, kp: int) -> _lib.PW:
+        w = sd[key]                                                     # (co, ci, ky, kx)
+        rows = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)            # [co][(ky,kx,ci)]
+        if rows.shape[1] < kp:
+            rows = torch.cat([rows, torch.zeros((rows.shape[0], kp - rows.shape[1]), dtype=rows.dtype)], dim=1)
+        return fold(rows, bn_prefix)
+
+    def sep(dst, prefix: str, bn_prefix: str):
+        dw = sd[prefix + ".conv1.weight"][:, 0]                          # (c, ky, kx)
+        dst.dw_w = pk.p(dw.permute(1, 2, 0).reshape(9, dw.shape[0]), f32, device)
+        dst.pw = fold(sd[prefix + ".pointwise.weight"].flatten(1), bn_prefix)
+
+    W.conv1 = dense3x3("conv1.weight", "bn1", 32)
+    W.conv2 = dense3x3("conv2.weight", "bn2", 288)
+    unit, skip = 0, 0
+    for bi, (cin, cout, reps, stride, relu0, grow_first) in enumerate(XCEPTION_BLOCKS):
+        p = f"block{bi + 1}."
+        idx = 1 if relu0 else 0                                          # position of the first SeparableConv2d in `rep`
+        for _ in sep_channels(cin, cout, reps, grow_first):
+            sep(W.sep[unit], f"{p}rep.{idx}", f"{p}rep.{idx + 1}")
+            unit += 1
+            idx += 3
+        if cout != cin or stride != 1:
+            W.skip[skip] = fold(sd[p + "skip.weight"].flatten(1), p + "skipbn")
+            skip += 1
+    sep(W.sep[unit], "conv3", "bn3")
+    sep(W.sep[unit + 1], "conv4", "bn4")
+    assert unit + 2 == 34 and skip == 4
     pk.struct = W
     return pk
 

@@ -114,3 +114,26 @@ def extractor_train_inputs():
     x = frames.view(4, 224, 224, 3).permute(0, 3, 1, 2).contiguous()
     probe = torch.randn((4, 1280, 7, 7), generator=torch.Generator().manual_seed(3))
     return esd, x, probe
+
+
+# ---------------------------------------------------------------------------------------------------
+# Xception extractor (oracle/make_golden_xception.py)
+# ---------------------------------------------------------------------------------------------------
+XCEPTION_STAGES = ["conv2"] + [f"block{i}" for i in range(1, 13)]
+
+
+def xception_inputs():
+    """(state_dict, 2 faces (2,3,224,224) raw 0..255) behind tests/golden/xception_b2.npz"""
+    sd = synth.make_xception_state_dict(2468)
+    meta = synth.make_batch_meta(1, 2, [1], seed=21, pad_tail=False)
+    frames = synth.make_frames(1, 2, seed=21, mask=meta["mask"])
+    return sd, frames.view(2, 224, 224, 3).permute(0, 3, 1, 2).contiguous()
+
+
+def xception_tsf_inputs():
+    """(cfg, xception sd, tsf sd, meta, frames (1,8,224,224,3)) behind tests/golden/xception_tsf_b1_f8.npz"""
+    B, f = 1, 8
+    cfg = default_tsf_config(num_frames=f, channels=2048)
+    meta = synth.make_batch_meta(B, f, [2], seed=33, pad_tail=True)
+    frames = synth.make_frames(B, f, seed=33, mask=meta["mask"])
+    return cfg, synth.make_xception_state_dict(2468), synth.make_tsf_state_dict(cfg, 4321), meta, frames
