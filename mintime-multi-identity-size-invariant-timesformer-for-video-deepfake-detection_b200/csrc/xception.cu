@@ -46,19 +46,25 @@ __global__ void __launch_bounds__(256) xc_im2col3x3_kernel(const TI* __restrict_
 }
 
 // out[n][h][w][c] = sum_{ky,kx} relu?(in[n][y+ky-1][x+kx-1][c]) * wt[ky*3+kx][c]   (zero padding 1, stride 1)
+// A thread owns 8 consecutive channels of one pixel (one 16-byte load per tap on the bf16 path); lanes run over channel
+// groups, so a warp reads whole contiguous channel rows; the 9x re-read of the input is served by L1/L2.  (A sliding-window
+// variant -- 8 output pixels per thread, 3 loads per output -- measured 2x slower: 176 registers, one block per SM.)
+// c is a multiple of 8 for every Xception layer.
 template <typename T>
 __global__ void __launch_bounds__(256) xc_dw3x3_kernel(const T* __restrict__ in, const float* __restrict__ wt,
                                                        T* __restrict__ out, int n, int h, int w, int c, int relu_in) {
-  const int c2 = c >> 1;                                   // channel pairs (c is even for every Xception layer)
-  const size_t total = (size_t)n * h * w * c2;
+  const int c8 = c >> 3;
+  const size_t total = (size_t)n * h * w * c8;
   for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
-    const int cp = (int)(idx % c2) * 2;
-    const size_t pix = idx / c2;
+    const int cg = (int)(idx % c8) * 8;
+    const size_t pix = idx / c8;
     const int x = (int)(pix % w);
     const size_t t = pix / w;
     const int y = (int)(t % h);
     const int img = (int)(t / h);
-    float a0 = 0.f, a1 = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = y + ky - 1;
@@ -67,33 +73,33 @@ __global__ void __launch_bounds__(256) xc_dw3x3_kernel(const T* __restrict__ in,
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = x + kx - 1;
         if (ix < 0 || ix >= w) continue;
-        const T* p = in + (((size_t)img * h + iy) * w + ix) * c + cp;
-        float v0 = to_f(p[0]), v1 = to_f(p[1]);
-        if (relu_in) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-        const float2 wv = *reinterpret_cast<const float2*>(wt + (size_t)(ky * 3 + kx) * c + cp);
-        a0 = fmaf(v0, wv.x, a0);
-        a1 = fmaf(v1, wv.y, a1);
+        float v[8], wv[8];
+        load8(in + (((size_t)img * h + iy) * w + ix) * c + cg, v);
+        load8(wt + (size_t)(ky * 3 + kx) * c + cg, wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(relu_in ? fmaxf(v[i], 0.f) : v[i], wv[i], acc[i]);
       }
     }
-    T* o = out + pix * c + cp;
-    o[0] = from_f<T>(a0);
-    o[1] = from_f<T>(a1);
+    store8(out + pix * c + cg, acc);
   }
 }
 
-// MaxPool2d(kernel 3, stride 2, padding 1): ho = (h - 1) / 2 + 1; padded positions never win (-inf)
+// MaxPool2d(kernel 3, stride 2, padding 1): ho = (h - 1) / 2 + 1; padded positions never win (-inf).  8 channels per thread.
 template <typename T>
 __global__ void __launch_bounds__(256) xc_maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int h, int w,
                                                          int c, int ho, int wo) {
-  const size_t total = (size_t)n * ho * wo * c;
+  const int c8 = c >> 3;
+  const size_t total = (size_t)n * ho * wo * c8;
   for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
-    const int ch = (int)(idx % c);
-    const size_t pix = idx / c;
+    const int cg = (int)(idx % c8) * 8;
+    const size_t pix = idx / c8;
     const int ox = (int)(pix % wo);
     const size_t t = pix / wo;
     const int oy = (int)(t % ho);
     const int img = (int)(t / ho);
-    float m = -FLT_MAX;
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -FLT_MAX;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = oy * 2 + ky - 1;
@@ -102,10 +108,13 @@ __global__ void __launch_bounds__(256) xc_maxpool_kernel(const T* __restrict__ i
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * 2 + kx - 1;
         if (ix < 0 || ix >= w) continue;
-        m = fmaxf(m, to_f(in[(((size_t)img * h + iy) * w + ix) * c + ch]));
+        float v[8];
+        load8(in + (((size_t)img * h + iy) * w + ix) * c + cg, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
       }
     }
-    out[idx] = from_f<T>(m);
+    store8(out + pix * c + cg, m);
   }
 }
 
@@ -113,23 +122,53 @@ __global__ void __launch_bounds__(256) xc_maxpool_kernel(const T* __restrict__ i
 template <typename T>
 __global__ void __launch_bounds__(256) xc_gather2_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int h, int w,
                                                          int c, int ho, int wo, int relu_in) {
-  const size_t total = (size_t)n * ho * wo * c;
+  const int c8 = c >> 3;
+  const size_t total = (size_t)n * ho * wo * c8;
   for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
-    const int ch = (int)(idx % c);
-    const size_t pix = idx / c;
+    const int cg = (int)(idx % c8) * 8;
+    const size_t pix = idx / c8;
     const int ox = (int)(pix % wo);
     const size_t t = pix / wo;
     const int oy = (int)(t % ho);
     const int img = (int)(t / ho);
-    float v = to_f(in[(((size_t)img * h + 2 * oy) * w + 2 * ox) * c + ch]);
-    if (relu_in) v = fmaxf(v, 0.f);
-    out[idx] = from_f<T>(v);
+    float v[8];
+    load8(in + (((size_t)img * h + 2 * oy) * w + 2 * ox) * c + cg, v);
+    if (relu_in) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    store8(out + pix * c + cg, v);
+  }
+}
+
+// im2col of a 3x3 VALID convolution whose input has a multiple of 8 channels (conv2): one thread per (pixel, tap, 8 channels)
+template <typename T>
+__global__ void __launch_bounds__(256) xc_im2col3x3_c8_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int h, int w,
+                                                              int c, int s, int ho, int wo, int relu_in) {
+  const int c8 = c >> 3, per_pix = 9 * c8;
+  const size_t total = (size_t)n * ho * wo * per_pix;
+  for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+    const int q = (int)(idx % per_pix);
+    const size_t pix = idx / per_pix;
+    const int tap = q / c8, cg = (q - tap * c8) * 8;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int ox = (int)(pix % wo);
+    const size_t t = pix / wo;
+    const int oy = (int)(t % ho);
+    const int img = (int)(t / ho);
+    float v[8];
+    load8(in + (((size_t)img * h + oy * s + ky) * w + ox * s + kx) * c + cg, v);
+    if (relu_in) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    store8(out + pix * (size_t)(9 * c) + (size_t)tap * c + cg, v);
   }
 }
 
 inline unsigned grid_for(size_t total) {
   const size_t blocks = (total + 255) / 256;
-  return (unsigned)std::min<size_t>(blocks, (size_t)current_sms() * 16);
+  return (unsigned)std::min<size_t>(blocks, (size_t)current_sms() * 32);
 }
 
 // geometry of the network at a given input size (224 in MINTIME): xception.py:105-131
@@ -208,9 +247,12 @@ int xc_forward(const mt_xception_weights_t* w, const void* x, int x_dtype, void*
   }
   // ---- conv2 3x3 s1 p0 (32 -> 64) + bn2 [+ relu, applied by block 1's consumers]       xception.py:109-111,152-154
   {
-    const size_t total = (size_t)n * g.h2 * g.h2 * 288;
-    xc_im2col3x3_kernel<T, T><<<grid_for(total), 256, 0, st>>>(A, col, n, g.h1, g.h1, 32, 1, g.h2, g.h2, 288, 1);
-    MT_LAUNCH_CHECK("xc_im2col3x3_kernel(conv2)");
+    const size_t total = (size_t)n * g.h2 * g.h2 * 36;
+    {
+      ProfScope ps(st, 0.0, ((double)n * g.h1 * g.h1 * 32 + (double)n * g.h2 * g.h2 * 288) * (double)sizeof(T), "xc_im2col conv2");
+      xc_im2col3x3_c8_kernel<T><<<grid_for(total), 256, 0, st>>>(A, col, n, g.h1, g.h1, 32, 1, g.h2, g.h2, 1);
+      MT_LAUNCH_CHECK("xc_im2col3x3_kernel(conv2)");
+    }
     rc = mt_pointwise_fwd(precision, col, w->conv2.w, w->conv2.shift, nullptr, 0, nullptr, 0, B, n * g.h2 * g.h2, 64, 288, stream);
     if (rc) return rc;
   }
@@ -233,9 +275,12 @@ int xc_forward(const mt_xception_weights_t* w, const void* x, int x_dtype, void*
       const int relu_in = (b == 1) ? 1 : ((r == 0) ? bk.relu0 : 1);   // block 1: its input is relu(bn2(.)) (xception.py:154)
       const mt_xc_sep_t& u = w->sep[unit];
       T* dwo = (src == t0) ? t1 : t0;
-      const size_t total = (size_t)rows_in * (ch / 2);
-      xc_dw3x3_kernel<T><<<grid_for(total), 256, 0, st>>>(src, u.dw_w, dwo, n, hin, hin, ch, relu_in);
-      MT_LAUNCH_CHECK("xc_dw3x3_kernel");
+      const size_t total = (size_t)rows_in * (ch / 8);
+      {
+        ProfScope ps(st, 18.0 * rows_in * ch, 2.0 * rows_in * ch * (double)sizeof(T), "xc_dw3x3 C%d H%d", ch, hin);
+        xc_dw3x3_kernel<T><<<grid_for(total), 256, 0, st>>>(src, u.dw_w, dwo, n, hin, hin, ch, relu_in);
+        MT_LAUNCH_CHECK("xc_dw3x3_kernel");
+      }
       T* pwo = (dwo == t0) ? t1 : t0;
       if (pwo == cur) return MT_ERR_ARG;   // (cannot happen: cur is never t0/t1 while a block runs)
       // identity-skip blocks add their input in the last unit's epilogue (xception.py:73-75)
@@ -251,10 +296,13 @@ int xc_forward(const mt_xception_weights_t* w, const void* x, int x_dtype, void*
       // MaxPool2d(3, 2, 1) on the main path, 1x1 stride-2 projection + BN of the block INPUT on the skip path, summed in the
       // projection's epilogue (xception.py:62-63, 68-76)
       T* pooled = (src == t0) ? t1 : t0;
-      const size_t tp = (size_t)n * hout * hout * ch;
-      xc_maxpool_kernel<T><<<grid_for(tp), 256, 0, st>>>(src, pooled, n, hin, hin, ch, hout, hout);
-      MT_LAUNCH_CHECK("xc_maxpool_kernel");
-      const size_t tg = (size_t)n * hout * hout * bk.cin;
+      const size_t tp = (size_t)n * hout * hout * (ch / 8);
+      {
+        ProfScope ps(st, 0.0, ((double)rows_in + (double)n * hout * hout) * ch * (double)sizeof(T), "xc_maxpool C%d H%d", ch, hin);
+        xc_maxpool_kernel<T><<<grid_for(tp), 256, 0, st>>>(src, pooled, n, hin, hin, ch, hout, hout);
+        MT_LAUNCH_CHECK("xc_maxpool_kernel");
+      }
+      const size_t tg = (size_t)n * hout * hout * (bk.cin / 8);
       xc_gather2_kernel<T><<<grid_for(tg), 256, 0, st>>>(cur, col, n, hin, hin, bk.cin, hout, hout, b == 1 ? 1 : 0);
       MT_LAUNCH_CHECK("xc_gather2_kernel");
       const int si = b <= 3 ? b - 1 : 3;
@@ -279,11 +327,11 @@ int xc_forward(const mt_xception_weights_t* w, const void* x, int x_dtype, void*
     const int hh = g.hb[12], rows = n * hh * hh;
     const mt_xc_sep_t& u3 = w->sep[unit];
     const mt_xc_sep_t& u4 = w->sep[unit + 1];
-    xc_dw3x3_kernel<T><<<grid_for((size_t)rows * 512), 256, 0, st>>>(cur, u3.dw_w, t0, n, hh, hh, 1024, 0);
+    xc_dw3x3_kernel<T><<<grid_for((size_t)rows * 128), 256, 0, st>>>(cur, u3.dw_w, t0, n, hh, hh, 1024, 0);
     MT_LAUNCH_CHECK("xc_dw3x3_kernel(conv3)");
     rc = mt_pointwise_fwd(precision, t0, u3.pw.w, u3.pw.shift, nullptr, 0, nullptr, 0, t1, rows, 1536, 1024, stream);
     if (rc) return rc;
-    xc_dw3x3_kernel<T><<<grid_for((size_t)rows * 768), 256, 0, st>>>(t1, u4.dw_w, t0, n, hh, hh, 1536, 1);
+    xc_dw3x3_kernel<T><<<grid_for((size_t)rows * 192), 256, 0, st>>>(t1, u4.dw_w, t0, n, hh, hh, 1536, 1);
     MT_LAUNCH_CHECK("xc_dw3x3_kernel(conv4)");
     rc = mt_pointwise_fwd(precision, t0, u4.pw.w, u4.pw.shift, nullptr, 0, nullptr, 0, feats, rows, 2048, 1536, stream);
     if (rc) return rc;
@@ -318,7 +366,6 @@ extern "C" int mt_xception_fwd(const mt_xception_weights_t* w, const void* x, in
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  ProfScope prof(st, 0.0, 0.0, "xception");
   return precision == MT_PREC_FP32 ? xc_forward<float>(w, x, x_dtype, feats, n_img, in_hw, precision, ws, st)
                                    : xc_forward<bf16>(w, x, x_dtype, feats, n_img, in_hw, precision, ws, st);
 }
