@@ -9,7 +9,8 @@
 //                                    [key][query], written transposed from the accumulator fragments)
 // The fragment / ldmatrix address patterns are the ones of attend_mtile (A from a row-major tile, B = rows of K for
 // Q K^T, B = .trans rows of V for P V); tiles are 128-byte rows with the 16-byte chunks XOR-swizzled by (row & 7).
-// The CLS query's contribution to dK / dV of the group's keys comes in through ws_kv (attn_cls_bwd_kernel), the group's
+// The CLS query's contribution to dK / dV of the group's keys comes in through ws_kv as (dS, p) per key and is rebuilt
+// as rank-1 products with q_cls / dO_cls (attn_cls_bwd_kernel), the group's
 // contribution to dK / dV of the CLS key leaves through ws_cls (attn_cls_finish_kernel sums them): see train.cu.
 #pragma once
 #include <float.h>
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(128) attn_group_bwd_mma_kernel(const bf16* __r
   const int h = valid ? (gidx / G) % heads : 0;
   const int b = valid ? gidx / (G * heads) : 0;
   const int N = 1 + f * n, inner = heads * 64, ld = 3 * inner;
-  const bf16* base = qkv + (size_t)b * N * ld + h * 64;
+  const bf16* base = qkv + (size_t)b * N * ld + h * 64;              // (token 0: base[0..63] is the CLS query)
+  const bf16* dcls = dout + (size_t)b * N * inner + h * 64;           // dO of the CLS row
   auto token = [&](int j) -> int {   // j = 0 CLS, j >= 1 the (j-1)-th member of the group
     if (j == 0) return 0;
     return MODE == MT_ATTN_TIME ? 1 + (j - 1) * n + g : 1 + g * n + (j - 1);
@@ -252,14 +254,17 @@ __global__ void __launch_bounds__(128) attn_group_bwd_mma_kernel(const bf16* __r
         }
       } else {
         const int tok = token(key);
-        const float* w = ws_kv + (bh * N + tok) * 128 + t * 2;
+        // the CLS query's rank-1 contribution: dS_cls,tok * q_cls and p_cls,tok * dO_cls
+        const float2 sp = *reinterpret_cast<const float2*>(ws_kv + (bh * N + tok) * 2);
         bf16* row = dqkv + ((size_t)b * N + tok) * ld + h * 64 + t * 2;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float2 ck = *reinterpret_cast<const float2*>(w + j * 8);
-          const float2 cv = *reinterpret_cast<const float2*>(w + 64 + j * 8);
-          *reinterpret_cast<uint32_t*>(row + inner + j * 8) = pack2(dk[j][half * 2] + ck.x, dk[j][half * 2 + 1] + ck.y);
-          *reinterpret_cast<uint32_t*>(row + 2 * inner + j * 8) = pack2(dv[j][half * 2] + cv.x, dv[j][half * 2 + 1] + cv.y);
+          const float2 qc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + t * 2 + j * 8));
+          const float2 oc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dcls + t * 2 + j * 8));
+          *reinterpret_cast<uint32_t*>(row + inner + j * 8) =
+              pack2(fmaf(sp.x, qc.x, dk[j][half * 2]), fmaf(sp.x, qc.y, dk[j][half * 2 + 1]));
+          *reinterpret_cast<uint32_t*>(row + 2 * inner + j * 8) =
+              pack2(fmaf(sp.y, oc.x, dv[j][half * 2]), fmaf(sp.y, oc.y, dv[j][half * 2 + 1]));
         }
       }
     }

@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(256) geglu_bwd_colsum_kernel(const T* __restri
 
 // ---------------------------------------------------------------------------------------------------
 // Attention core backward (Attention.forward :114-141, attn :80-87), probabilities recomputed from qkv.
-// Workspace (fp32):  ws_kv [B*heads][N][128]  CLS-row contribution to dK (0..63) and dV (64..127) of every key
+// Workspace (fp32):  ws_kv [B*heads][N][2]    (dS_j, p_j) of the CLS query for every key j: its contribution to dK_j / dV_j is
+//                                             the rank-1 pair dS_j * q_cls / p_j * dO_cls, rebuilt by the consumers (round 1
+//                                             wrote the 128 products per key: 103 MB per launch at B = 32)
 //                    ws_q  [B*heads][64]      dQ of the CLS query
 //                    ws_cls[B*heads][G][128]  per-group contribution to dK / dV of the CLS key
 // (1) attn_cls_bwd_kernel   : CLS query over all N keys            -> ws_kv, ws_q
@@ -427,24 +429,19 @@ __global__ void __launch_bounds__(256) attn_cls_bwd_kernel(const T* __restrict__
   for (int i = 0; i < 8; ++i) D += red[i];
   for (int j = tid; j < N; j += 256) dp[j] = sc[j] * (dp[j] - D);   // dS_j (each thread rewrites its own entries)
   __syncthreads();
-  // thread = (key lane kg of 32, 8-dim chunk dc): dK_j += dS_j q0, dV_j += p_j dO, dQ0 += dS_j K_j
+  // (dS_j, p_j) per key for the consumers; thread = (key lane kg of 32, 8-dim chunk dc): dQ0 += dS_j K_j
   const int dc = tid & 7, kg = tid >> 3;
-  float acc[8], qd[8], od[8];
+  float acc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { acc[i] = 0.f; qd[i] = q0[dc * 8 + i]; od[i] = d0[dc * 8 + i]; }
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int j = tid; j < N; j += 256)
+    *reinterpret_cast<float2*>(ws_kv + ((size_t)blockIdx.x * N + j) * 2) = make_float2(dp[j], sc[j]);
   for (int j = kg; j < N; j += 32) {
-    float kv[8], t[8];
+    float kv[8];
     load8(base + (size_t)j * ld + inner + h * 64 + dc * 8, kv);
-    const float ds = dp[j], pj = sc[j];
+    const float ds = dp[j];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = fmaf(ds, kv[i], acc[i]);
-    float* w = ws_kv + ((size_t)blockIdx.x * N + j) * 128;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = ds * qd[i];
-    store8(w + dc * 8, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = pj * od[i];
-    store8(w + 64 + dc * 8, t);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[kg * 64 + dc * 8 + i] = acc[i];
@@ -547,7 +544,9 @@ __global__ void __launch_bounds__(128) attn_group_bwd_kernel(const T* __restrict
   }
   __syncthreads();
   // phase 2: dK_j = sum_i dS_ij Q_i, dV_j = sum_i P_ij dO_i  (+ the CLS-row contribution of ws_kv), fixed order
-  const float* wkv = ws_kv + (size_t)(b * heads + h) * N * 128;
+  const float* wkv = ws_kv + (size_t)(b * heads + h) * N * 2;
+  const T* q_cls = qkv + (size_t)b * N * ld + h * 64;                  // the CLS query (pre-scaled) and its dO
+  const T* d_cls = dout + (size_t)b * N * inner + h * 64;
   for (int e = tid; e < Gk * 64; e += 128) {
     const int j = e >> 6, d = e & 63;
     float dk = 0.f, dv = 0.f;
@@ -561,8 +560,9 @@ __global__ void __launch_bounds__(128) attn_group_bwd_kernel(const T* __restrict
       w[64 + d] = dv;
     } else {
       const int tok = token(j);
-      dk += wkv[(size_t)tok * 128 + d];
-      dv += wkv[(size_t)tok * 128 + 64 + d];
+      const float2 sp = *reinterpret_cast<const float2*>(wkv + (size_t)tok * 2);
+      dk = fmaf(sp.x, to_f(q_cls[d]), dk);
+      dv = fmaf(sp.y, to_f(d_cls[d]), dv);
       T* row = dqkv + ((size_t)b * N + tok) * ld + h * 64 + d;
       row[inner] = from_f<T>(dk);
       row[2 * inner] = from_f<T>(dv);
@@ -571,12 +571,14 @@ __global__ void __launch_bounds__(128) attn_group_bwd_kernel(const T* __restrict
 }
 
 template <typename T>
-__global__ void __launch_bounds__(64) attn_cls_finish_kernel(T* __restrict__ dqkv, const float* __restrict__ ws_kv,
+__global__ void __launch_bounds__(64) attn_cls_finish_kernel(T* __restrict__ dqkv, const T* __restrict__ qkv,
+                                                             const T* __restrict__ dout, const float* __restrict__ ws_kv,
                                                              const float* __restrict__ ws_q,
                                                              const float* __restrict__ ws_cls, int N, int G, int heads) {
   const int b = blockIdx.x / heads, h = blockIdx.x % heads, d = threadIdx.x;
   const int inner = heads * 64, ld = 3 * inner;
-  float dk = ws_kv[(size_t)blockIdx.x * N * 128 + d], dv = ws_kv[(size_t)blockIdx.x * N * 128 + 64 + d];
+  const float2 sp = *reinterpret_cast<const float2*>(ws_kv + (size_t)blockIdx.x * N * 2);    // the CLS key seen by the CLS query
+  float dk = sp.x * to_f(qkv[(size_t)b * N * ld + h * 64 + d]), dv = sp.y * to_f(dout[(size_t)b * N * inner + h * 64 + d]);
   for (int g = 0; g < G; ++g) {
     dk += ws_cls[((size_t)blockIdx.x * G + g) * 128 + d];
     dv += ws_cls[((size_t)blockIdx.x * G + g) * 128 + 64 + d];
@@ -592,7 +594,7 @@ AttnBwdWs attn_bwd_ws(int B, int f, int n, int heads) {
   const size_t N = 1 + (size_t)f * n, bh = (size_t)B * heads;
   AttnBwdWs l;
   l.kv = 0;
-  l.q = l.kv + bh * N * 128 * 4;
+  l.q = l.kv + ((bh * N * 2 * 4 + 255) & ~(size_t)255);
   l.cls = l.q + bh * 64 * 4;
   l.total = l.cls + bh * (size_t)std::max(f, n) * 128 * 4;
   return l;
@@ -610,8 +612,8 @@ int launch_attn_bwd(const void* qkv_, const void* dout_, const uint8_t* mask, co
   float* ws_q = reinterpret_cast<float*>(ws + l.q);
   float* ws_cls = reinterpret_cast<float*>(ws + l.cls);
   {
-    // K, V of every token read once, the fp32 dK / dV contributions of the CLS row written once
-    ProfScope prof(st, 10.0 * B * heads * 64.0 * N, (double)B * N * heads * (64.0 * 2 * sizeof(T) + 512.0), "attn_cls_bwd");
+    // K of every token read twice (scores, dQ), V once; two floats per key written
+    ProfScope prof(st, 10.0 * B * heads * 64.0 * N, (double)B * N * heads * (64.0 * 3 * sizeof(T) + 8.0), "attn_cls_bwd");
     const size_t smem = (size_t)(2 * N + 64 + 64 + 32 + 2048) * sizeof(float);
     auto kern = attn_cls_bwd_kernel<T>;
     if (smem > 48 * 1024) {
@@ -653,7 +655,7 @@ int launch_attn_bwd(const void* qkv_, const void* dout_, const uint8_t* mask, co
     }
     if (rc_mma != MT_OK) MT_LAUNCH_CHECK("attn_group_bwd_kernel");
   }
-  attn_cls_finish_kernel<T><<<B * heads, 64, 0, st>>>(dqkv, ws_kv, ws_q, ws_cls, N, G, heads);
+  attn_cls_finish_kernel<T><<<B * heads, 64, 0, st>>>(dqkv, qkv, dout, ws_kv, ws_q, ws_cls, N, G, heads);
   MT_LAUNCH_CHECK("attn_cls_finish_kernel");
   return MT_OK;
 }
