@@ -27,7 +27,7 @@ extern "C" {
 #define MT_ABI_VERSION 5   /* 2: mt_divided_attn_fwd takes a workspace; + mt_expand_dwconv_*, mt_clip_meta_fwd
                             * 3: + the backward entry points of the transformer (mt_*_bwd, mt_grad_prep, mt_geglu_*)
                             * 4: mt_clip_meta_fwd mask_padding semantics; fused divided attention; extractor training
-                            * 5: + mt_linear_wgrad_nt (weight gradient from row-major operands), mt_geglu_bwd_colsum, mt_xception_* */
+                            * 5: + mt_linear_wgrad_nt (weight gradient from row-major operands), mt_geglu_bwd_colsum, mt_layernorm_copy_fwd, mt_xception_* */
 
 enum { MT_PREC_FP32 = 0, MT_PREC_BF16 = 1 };
 enum { MT_OK = 0, MT_ERR_ARG = -1, MT_ERR_WORKSPACE = -2, MT_ERR_UNSUPPORTED = -3, MT_ERR_DRIVER = -4 };
@@ -187,6 +187,10 @@ int mt_patch_embed_fwd(int precision, const mt_tsf_weights_t* w, const mt_tsf_cf
 /* nn.LayerNorm(dim) over the last axis, eps 1e-5 (:18-26): f32 [rows][dim] -> T [rows][dim] */
 int mt_layernorm_fwd(int precision, const float* x, const float* gamma, const float* beta, void* out, int rows,
                      int dim, void* stream);
+/* The same, also writing x_copy f32 [rows][dim] = x (the training forward keeps every sub-block's input for the LayerNorm
+ * backward; the residual GEMM that follows updates x in place).  x_copy may be NULL. */
+int mt_layernorm_copy_fwd(int precision, const float* x, const float* gamma, const float* beta, void* out, float* x_copy,
+                          int rows, int dim, void* stream);
 
 /* Attention core of Attention.forward (:114-141) on an already projected qkv (q pre-scaled):
  *   qkv T [B][1+f*n][3*heads*dim_head] -> out T [B][1+f*n][heads*dim_head] (heads merged, before to_out)

@@ -20,7 +20,7 @@ EXPORTS = [
     "mt_abi_version", "mt_last_error", "mt_device_check",
     "mt_effnet_b0_workspace_bytes", "mt_effnet_b0_fwd", "mt_xception_out_hw", "mt_xception_workspace_bytes", "mt_xception_fwd", "mt_tsf_workspace_bytes", "mt_tsf_fwd",
     "mt_pointwise_fwd", "mt_linear_residual_fwd", "mt_linear_geglu_fwd", "mt_patch_embed_fwd",
-    "mt_layernorm_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_fused_attn_supported",
+    "mt_layernorm_fwd", "mt_layernorm_copy_fwd", "mt_divided_attn_fwd", "mt_divided_attn_workspace_bytes", "mt_fused_attn_supported",
     "mt_fused_attn_workspace_bytes", "mt_fused_attn_fwd", "mt_stem_fwd", "mt_dwconv_fwd", "mt_se_gate_fwd", "mt_head_fwd",
     "mt_dwconv_chunks", "mt_expand_dwconv_chunks", "mt_expand_dwconv_fwd", "mt_effnet_b0_block_spec", "mt_mbconv_workspace_bytes", "mt_mbconv_fwd",
     "mt_aggregate_attn_fwd", "mt_clip_meta_fwd",
@@ -117,6 +117,7 @@ def load() -> C.CDLL:
     lib.mt_linear_geglu_fwd.argtypes = [i32, vp, vp, fp, vp, i32, i32, i32, vp]
     lib.mt_patch_embed_fwd.argtypes = [i32, C.POINTER(TsfWeights), C.POINTER(TsfCfg), vp, vp, vp, fp, i32, vp]
     lib.mt_layernorm_fwd.argtypes = [i32, fp, fp, fp, vp, i32, i32, vp]
+    lib.mt_layernorm_copy_fwd.argtypes = [i32, fp, fp, fp, vp, fp, i32, i32, vp]
     lib.mt_divided_attn_fwd.argtypes = [i32, vp, vp, vp, i32, vp, fp, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.mt_divided_attn_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.mt_divided_attn_workspace_bytes.restype = sz

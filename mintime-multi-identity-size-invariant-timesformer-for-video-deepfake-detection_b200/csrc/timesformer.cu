@@ -32,8 +32,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // and writes the current one (the one-row-per-warp version ran at 43 % occupancy and 3 TB/s: blocks lived ~1 us).
 template <typename T, int NV>   // NV = dim / 128 float4 per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                                                        const float* __restrict__ b, T* __restrict__ out, int rows,
-                                                        int dim) {
+                                                        const float* __restrict__ b, T* __restrict__ out,
+                                                        float* __restrict__ x_copy, int rows, int dim) {
   const int lane = threadIdx.x & 31;
   const int wstride = gridDim.x * 8;
   int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -69,6 +69,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
     const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)dim + 1e-5f);
     T* orow = out + (size_t)row * dim;
+    if (x_copy != nullptr) {          // training: the sub-block's input survives the in-place residual update that follows
+      float4* cr = reinterpret_cast<float4*>(x_copy + (size_t)row * dim);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) cr[i * 32 + lane] = v[i];
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c0 = (i * 32 + lane) * 4;
@@ -409,6 +414,11 @@ using namespace mt;
 
 extern "C" int mt_layernorm_fwd(int precision, const float* x, const float* gamma, const float* beta, void* out,
                                 int rows, int dim, void* stream) {
+  return mt_layernorm_copy_fwd(precision, x, gamma, beta, out, nullptr, rows, dim, stream);
+}
+
+extern "C" int mt_layernorm_copy_fwd(int precision, const float* x, const float* gamma, const float* beta, void* out,
+                                     float* x_copy, int rows, int dim, void* stream) {
   MT_REQUIRE(x && gamma && beta && out && rows > 0, "layernorm: bad argument");
   MT_REQUIRE(dim % 128 == 0 && dim <= 1024, "layernorm: dim must be a multiple of 128 <= 1024 (got %d)", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -416,9 +426,9 @@ extern "C" int mt_layernorm_fwd(int precision, const float* x, const float* gamm
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min((rows + 7) / 8, sms * 6);      // persistent: <= 6 blocks (48 warps) per SM
-  ProfScope prof(st, 8.0 * rows * dim, (double)rows * dim * (4 + (precision == MT_PREC_FP32 ? 4 : 2)), "layernorm");
+  ProfScope prof(st, 8.0 * rows * dim, (double)rows * dim * (4 + (x_copy ? 4 : 0) + (precision == MT_PREC_FP32 ? 4 : 2)), "layernorm");
   const int nv = dim >> 7;
-#define MT_LN_LAUNCH(TT, NVV) layernorm_kernel<TT, NVV><<<grid, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<TT*>(out), rows, dim)
+#define MT_LN_LAUNCH(TT, NVV) layernorm_kernel<TT, NVV><<<grid, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<TT*>(out), x_copy, rows, dim)
   if (precision != MT_PREC_FP32 && precision != MT_PREC_BF16) {
     set_error("layernorm: unknown precision %d", precision);
     return MT_ERR_ARG;

@@ -81,6 +81,20 @@ def layernorm(x, gamma, beta, precision="bf16"):
     return out
 
 
+def layernorm_copy(x, gamma, beta, precision="bf16"):
+    """(LayerNorm(x), a float32 copy of x) in one pass: the training forward keeps the sub-block input this way"""
+    _prep(x, torch.float32)
+    rows, dim = x.shape
+    _lib.require_device(x.device)
+    out = torch.empty((rows, dim), dtype=_T(precision), device=x.device)
+    x_copy = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mt_layernorm_copy_fwd(_lib.prec_id(precision), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                               out.data_ptr(), x_copy.data_ptr(), rows, dim, _lib.stream_ptr())
+    _lib.check(rc, "mt_layernorm_copy_fwd")
+    return out, x_copy
+
+
 def divided_attention(qkv, mask_u8, idmask_u8, mode: str, f: int, n: int, heads: int, dim_head: int = 64,
                       want_cls_attn: bool = True, precision="bf16"):
     """qkv (B, 1+f*n, 3*heads*dim_head) with q pre-scaled -> (out (B,N,heads*dim_head), cls_attn (B*heads,N))"""

@@ -194,8 +194,7 @@ class TsfTrainFunction(torch.autograd.Function):
             S = {}
             for name in ("time", "space"):
                 want_maps = model.require_attention and l == len(pk.layers) - 1
-                x_in = x.clone()
-                xn = ops.layernorm(x_in, L[name + ".ln_g"], L[name + ".ln_b"], precision)
+                xn, x_in = ops.layernorm_copy(x, L[name + ".ln_g"], L[name + ".ln_b"], precision)   # (x is updated in place below)
                 qkv = ops.pointwise(xn, L[name + ".wqkv"], precision=precision)
                 ao, cls = ops.divided_attention(qkv.view(B, N, -1), mask_u8, idm_u8, name, f, n, heads, dh,
                                                 want_cls_attn=want_maps, precision=precision)
@@ -204,8 +203,7 @@ class TsfTrainFunction(torch.autograd.Function):
                 S[name] = (x_in, xn, qkv, ao)
                 if want_maps:
                     maps[name] = cls.view(B * heads, 1, N)
-            x_in = x.clone()
-            xn = ops.layernorm(x_in, L["ff.ln_g"], L["ff.ln_b"], precision)
+            xn, x_in = ops.layernorm_copy(x, L["ff.ln_g"], L["ff.ln_b"], precision)
             h = ops.pointwise(xn, L["ff.w1"], shift=L["ff.b1"], precision=precision)
             go = ops.geglu(h, precision)
             ops.linear_residual_(x, go, L["ff.w2"], L["ff.b2"], precision)

@@ -123,6 +123,9 @@ def test_layernorm(prec):
     out = ops.layernorm(x.to(DEV), g.to(DEV), b.to(DEV), precision=prec)
     torch.cuda.synchronize()
     assert rel_err(out.float().cpu(), ref) <= tol(prec, 2e-6, 3e-3)
+    out2, xc = ops.layernorm_copy(x.to(DEV), g.to(DEV), b.to(DEV), precision=prec)    # training forward: + a copy of the input
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out) and torch.equal(xc.cpu(), x)
 
 
 @pytest.mark.parametrize("prec", PRECS)
