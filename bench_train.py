@@ -158,7 +158,7 @@ def run_train(args, emit, ClockSampler, load_peaks):
                 else:
                     p.requires_grad_(name.startswith(("_conv_head", "_bn1")))
         if world > 1:
-            raise SystemExit("--unfrozen is a single-GPU measurement for now (the extractor's gradients are not bucketed)")
+            training.attach_grad_sync(ext)                              # one averaged bucket for the extractor's gradients
     model = mintime_b200.SizeInvariantTimeSformer(config=cfg, precision=args.precision)
     model.load_state_dict(synth.make_tsf_state_dict(cfg, 4321))
     model = model.to(dev).train()                                       # train.py:315

@@ -294,6 +294,20 @@ class EffnetTrainFunction(torch.autograd.Function):
     @staticmethod
     def _pack(ctx, G):
         out = [None, None, None]
+        live = [(name, p) for name, p in zip(ctx.names, ctx.ext.parameters()) if p.requires_grad and G.get(name) is not None]
+        sync = getattr(ctx.ext, "_grad_sync", None)
+        if sync is not None and live:
+            # data parallel (training.attach_grad_sync(extractor)): the extractor's gradients travel as ONE flat fp32 bucket,
+            # averaged over the ranks before autograd sees them; the views handed back alias the bucket
+            flat = torch.empty((sum(G[name].numel() for name, _ in live),), dtype=f32, device=G[live[0][0]].device)
+            off = 0
+            for name, _ in live:
+                k = G[name].numel()
+                flat[off:off + k].copy_(G[name].reshape(-1))
+                G[name] = flat[off:off + k]
+                off += k
+            sync.launch(flat)
+            sync.finish()
         for name, p in zip(ctx.names, ctx.ext.parameters()):
             g = G.get(name)
             out.append(g.view_as(p) if (g is not None and p.requires_grad) else None)

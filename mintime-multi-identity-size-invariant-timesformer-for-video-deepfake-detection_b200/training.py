@@ -136,9 +136,10 @@ class GradSync:
 
 
 def attach_grad_sync(model, group=None, broadcast_parameters: bool = True):
-    """Average the gradients over the ranks of `group` inside every backward of `model` (data parallel training).
-    Like DistributedDataParallel, rank 0's parameters are broadcast first so the replicas start identical whatever each
-    rank seeded."""
+    """Average the gradients over the ranks of `group` inside every backward of `model` (data parallel training): the
+    ``SizeInvariantTimeSformer`` (per-layer buckets) or an ``EfficientNet`` in train mode (one bucket; BatchNorm statistics
+    stay per replica, as under the reference's ``nn.DataParallel``).  Like DistributedDataParallel, rank 0's parameters and
+    buffers are broadcast first so the replicas start identical whatever each rank seeded."""
     model._grad_sync = GradSync(group)
     if broadcast_parameters and model._grad_sync.world > 1:
         import torch.distributed as dist
@@ -146,6 +147,8 @@ def attach_grad_sync(model, group=None, broadcast_parameters: bool = True):
         with torch.no_grad():
             for p in model.parameters():
                 dist.broadcast(p.data, src=src, group=group)
+            for b in model.buffers():            # (the extractor's BatchNorm running statistics; DDP broadcasts buffers too)
+                dist.broadcast(b.data, src=src, group=group)
         model._train_pack = None
         model._packed = None
     return model

@@ -164,3 +164,50 @@ def test_attach_grad_sync_broadcasts_rank0_parameters_and_rejects_copies():
     assert res[0][1] != res[1][1]                       # different seeds
     assert res[0][2] == res[1][2] == res[0][1]          # both hold rank 0's values afterwards
     assert all("contiguous" in r[3] for r in res)
+
+
+def _extractor_sync_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import mintime_b200  # noqa: F401
+    from mintime_b200 import training
+    from mintime_b200.efficientnet_train import EffnetTrainFunction
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(7 + rank)
+    ext = torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.BatchNorm1d(2))     # stands in for the extractor's containers
+    ext[1].running_mean.fill_(float(rank + 1))
+    training.attach_grad_sync(ext)                       # parameters AND buffers of rank 0 everywhere
+    ext[1].weight.requires_grad_(False)                  # a frozen tensor gets no gradient and is not exchanged
+
+    class Ctx:
+        pass
+
+    ctx = Ctx()
+    ctx.ext, ctx.names = ext, [k for k, _ in ext.named_parameters()]
+    G = {"0.weight": torch.full((2, 3), float(rank + 1)), "0.bias": torch.full((2,), 10.0 * (rank + 1)),
+         "1.weight": torch.full((2,), 99.0), "1.bias": torch.full((2,), float(rank))}
+    out = EffnetTrainFunction._pack(ctx, G)
+    q.put((rank, float(ext[1].running_mean[0]), [None if o is None else float(o.flatten()[0]) for o in out],
+           float(ext[0].weight.double().sum())))
+    dist.destroy_process_group()
+
+
+def test_extractor_gradients_are_averaged_over_ranks():
+    """an unfrozen extractor under data parallelism (train.py:153-170 + :294-296): attach_grad_sync(extractor) broadcasts
+    rank 0's parameters and BatchNorm buffers, and the backward's gradients leave as one averaged bucket"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_extractor_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] == 1.0                 # rank 0's running_mean
+    assert res[0][3] == res[1][3]                        # rank 0's weights
+    for r in res:
+        assert r[2] == [None, None, None, 1.5, 15.0, None, 0.5]
