@@ -204,7 +204,7 @@ def run_train(args, emit, ClockSampler, load_peaks):
     # The step (extractor, forward, backward incl. the per-layer NCCL all-reduces under data parallelism) replays as ONE
     # CUDA graph (mintime_b200.graphed.GraphedTrainStep) followed by the eager optimizer step; the fully eager step is
     # bound by its ~900 host-side launches.
-    use_graph = not args.no_graph and not unfrozen
+    use_graph = not args.no_graph
     graph_kernels = 0
     if use_graph:
         from mintime_b200.graphed import GraphedTrainStep

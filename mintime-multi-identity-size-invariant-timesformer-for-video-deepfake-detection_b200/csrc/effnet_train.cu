@@ -170,11 +170,16 @@ __global__ void __launch_bounds__(864) stem_wgrad_kernel(const float* __restrict
   const long long rows = (long long)n * Ho * Wo;
   const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   double acc = 0.0;
+  // (ox, oy, img) walk with the row index: one decode per block instead of three 64-bit divisions per row
+  int ox = (int)(r0 % Wo), oy = (int)((r0 / Wo) % Ho), img = (int)(r0 / ((long long)Wo * Ho));
   for (long long r = r0; r < r1; ++r) {
-    const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), img = (int)(r / ((long long)Wo * Ho));
     const int iy = oy * 2 + ky - pad, ix = ox * 2 + kx - pad;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    acc += (double)dy[(size_t)r * 32 + co] * (double)x[(((size_t)img * H + iy) * W + ix) * 3 + ci];
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      acc += (double)dy[(size_t)r * 32 + co] * (double)x[(((size_t)img * H + iy) * W + ix) * 3 + ci];
+    if (++ox == Wo) {
+      ox = 0;
+      if (++oy == Ho) { oy = 0; ++img; }
+    }
   }
   partial[(size_t)blockIdx.x * 864 + threadIdx.x] = acc;
 }
@@ -188,10 +193,11 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
   out[j] = (float)s;
 }
 
-// ---- depthwise kxk stride s, raw; w tap-major [k*k][C]
+// ---- depthwise kxk stride s, raw; w tap-major [k*k][C].  K and S are compile-time: with run-time values the tap loops carried
+// an integer division / modulo per tap (dgrad: 1 ms per layer at 128 images).
+template <int K, int S>
 __global__ void __launch_bounds__(256) dw_raw_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                         float* __restrict__ out, int n, int H, int Ho, int C, int K, int S,
-                                                         int pad) {
+                                                         float* __restrict__ out, int n, int H, int Ho, int C, int pad) {
   const size_t total = (size_t)n * Ho * Ho * C;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -200,9 +206,11 @@ __global__ void __launch_bounds__(256) dw_raw_fwd_kernel(const float* __restrict
     const int oy = (int)(p % Ho);
     const int img = (int)(p / Ho);
     float acc = 0.f;
+#pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int iy = oy * S + ky - pad;
       if (iy < 0 || iy >= H) continue;
+#pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         const int ix = ox * S + kx - pad;
         if (ix < 0 || ix >= H) continue;
@@ -214,9 +222,9 @@ __global__ void __launch_bounds__(256) dw_raw_fwd_kernel(const float* __restrict
 }
 
 // dx[n][iy][ix][c] = sum over taps of dy[n][oy][ox][c] * w[ky][kx][c] with iy = oy*S + ky - pad
+template <int K, int S>
 __global__ void __launch_bounds__(256) dw_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                       float* __restrict__ dx, int n, int H, int Ho, int C, int K, int S,
-                                                       int pad) {
+                                                       float* __restrict__ dx, int n, int H, int Ho, int C, int pad) {
   const size_t total = (size_t)n * H * H * C;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -225,15 +233,17 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const float* __restrict__
     const int iy = (int)(p % H);
     const int img = (int)(p / H);
     float acc = 0.f;
+#pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int ty = iy + pad - ky;
-      if (ty < 0 || ty % S) continue;
-      const int oy = ty / S;
+      if (ty < 0 || (S == 2 && (ty & 1))) continue;
+      const int oy = S == 2 ? ty >> 1 : ty;
       if (oy >= Ho) continue;
+#pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         const int tx = ix + pad - kx;
-        if (tx < 0 || tx % S) continue;
-        const int ox = tx / S;
+        if (tx < 0 || (S == 2 && (tx & 1))) continue;
+        const int ox = S == 2 ? tx >> 1 : tx;
         if (ox >= Ho) continue;
         acc = fmaf(dy[(((size_t)img * Ho + oy) * Ho + ox) * C + c], w[(ky * K + kx) * C + c], acc);
       }
@@ -257,7 +267,8 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__
   for (int t = 0; t < K * K; ++t) acc[t] = 0.0;
   if (c < C) {
     for (long long p = p0 + rl; p < p1; p += kRedRows) {
-      const int ox = (int)(p % Ho), oy = (int)((p / Ho) % Ho), img = (int)(p / ((long long)Ho * Ho));
+      const unsigned pp = (unsigned)p;                      // (npos < 2^31: 32-bit divisions)
+      const int ox = (int)(pp % (unsigned)Ho), oy = (int)((pp / (unsigned)Ho) % (unsigned)Ho), img = (int)(pp / (unsigned)(Ho * Ho));
       const float g = dy[(size_t)p * C + c];
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
@@ -578,8 +589,12 @@ extern "C" int mt_dwconv_raw_fwd(const float* in, const float* w, float* out, in
   MT_REQUIRE(in && w && out && n_img > 0 && h > 0 && c > 0 && (k == 3 || k == 5) && (s == 1 || s == 2), "dwconv_raw_fwd: bad argument");
   const int Ho = (h + s - 1) / s;
   const size_t total = (size_t)n_img * Ho * Ho * c;
-  dw_raw_fwd_kernel<<<ew_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, w, out, n_img, h, Ho, c, k, s,
-                                                                                        same_pad_lo_t(h, k, s));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int pad = same_pad_lo_t(h, k, s), grid = ew_grid(total);
+  if (k == 3 && s == 1) dw_raw_fwd_kernel<3, 1><<<grid, 256, 0, st>>>(in, w, out, n_img, h, Ho, c, pad);
+  else if (k == 3) dw_raw_fwd_kernel<3, 2><<<grid, 256, 0, st>>>(in, w, out, n_img, h, Ho, c, pad);
+  else if (s == 1) dw_raw_fwd_kernel<5, 1><<<grid, 256, 0, st>>>(in, w, out, n_img, h, Ho, c, pad);
+  else dw_raw_fwd_kernel<5, 2><<<grid, 256, 0, st>>>(in, w, out, n_img, h, Ho, c, pad);
   MT_LAUNCH_CHECK("dw_raw_fwd_kernel");
   return MT_OK;
 }
@@ -588,8 +603,12 @@ extern "C" int mt_dwconv_dgrad(const float* dy, const float* w, float* dx, int n
   MT_REQUIRE(dy && w && dx && n_img > 0 && h > 0 && c > 0 && (k == 3 || k == 5) && (s == 1 || s == 2), "dwconv_dgrad: bad argument");
   const int Ho = (h + s - 1) / s;
   const size_t total = (size_t)n_img * h * h * c;
-  dw_dgrad_kernel<<<ew_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, w, dx, n_img, h, Ho, c, k, s,
-                                                                                      same_pad_lo_t(h, k, s));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int pad = same_pad_lo_t(h, k, s), grid = ew_grid(total);
+  if (k == 3 && s == 1) dw_dgrad_kernel<3, 1><<<grid, 256, 0, st>>>(dy, w, dx, n_img, h, Ho, c, pad);
+  else if (k == 3) dw_dgrad_kernel<3, 2><<<grid, 256, 0, st>>>(dy, w, dx, n_img, h, Ho, c, pad);
+  else if (s == 1) dw_dgrad_kernel<5, 1><<<grid, 256, 0, st>>>(dy, w, dx, n_img, h, Ho, c, pad);
+  else dw_dgrad_kernel<5, 2><<<grid, 256, 0, st>>>(dy, w, dx, n_img, h, Ho, c, pad);
   MT_LAUNCH_CHECK("dw_dgrad_kernel");
   return MT_OK;
 }

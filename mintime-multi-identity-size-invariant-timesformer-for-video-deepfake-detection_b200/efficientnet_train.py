@@ -7,7 +7,8 @@ statistics (utils.py:520-521: momentum 0.01, eps 1e-3), and every skip block app
 ``0.2 * idx / 16`` (model.py:125-127, 279-282; utils.py:129-154).  So nothing can be folded into the convolution weights:
 the forward keeps every raw convolution output, its batch statistics and the activated tensors, and the backward walks the
 layers in reverse through the kernels of csrc/effnet_train.cu (BatchNorm / swish / depthwise / squeeze-excite backward)
-and the library's GEMMs (1x1 convolutions: data gradient by mt_pointwise_fwd on W^T, weight gradient by mt_conv1x1_wgrad).
+and the library's GEMMs (1x1 convolutions: data gradient by mt_pointwise_fwd on W^T, weight gradient by mt_conv1x1_wgrad;
+with ``precision="bf16"`` these GEMMs run on the tensor cores with bf16 operands and fp32 accumulation -- see ``pw``).
 
 Exposed as ONE ``torch.autograd.Function`` so the reference loop (``loss.backward(); optimizer.step()``) works unchanged.
 Arithmetic is fp32 (the exact path); there is no PyTorch fallback.  Gradients stop at the first layer that still has a
@@ -81,10 +82,23 @@ def bn_act_bwd(dy2d, x2d, mean, var, gamma, beta, act: int, ws: _Ws):
     return dx, dg, db
 
 
-def conv1x1_wgrad(dy2d, a2d):
-    """dW [cout, cin] = dy^T a  (both [rows, *] fp32)"""
+def pw(precision, x2d, w2d, **kw):
+    """1x1 convolution / its data gradient on fp32 [rows, cin] activations.  precision "fp32": the exact FFMA GEMM (what the
+    reference-fixture tests run); "bf16": operands cast to bf16, tcgen05 GEMM with fp32 accumulation, fp32 result -- the
+    mixed-precision mode of the bf16 extractor (the batch statistics, the normalisation and every other step stay fp32)."""
+    if precision == "bf16" and x2d.shape[1] % 8 == 0 and w2d.shape[0] % 8 == 0:
+        return ops.pointwise(x2d.bfloat16(), w2d.bfloat16(), precision="bf16", **kw).float()
+    return ops.pointwise(x2d, w2d, precision="fp32", **kw)
+
+
+def conv1x1_wgrad(dy2d, a2d, precision="fp32"):
+    """dW [cout, cin] = dy^T a  (both [rows, *] fp32); bf16 mode: channel counts that are multiples of 64 (the 192 / 320 /
+    1152 / 1280-wide layers, most of the FLOPs) go through the MN-major tensor-core weight gradient"""
     rows, co = dy2d.shape
     ci = a2d.shape[1]
+    if precision == "bf16" and co % 64 == 0 and ci % 64 == 0:
+        dw = torch.zeros((co, ci), dtype=f32, device=dy2d.device)
+        return ops.linear_wgrad_nt_(dw, dy2d.bfloat16(), a2d.bfloat16())
     lib = _lib.load()
     ws = torch.empty((int(lib.mt_conv1x1_wgrad_workspace_bytes(rows, co, ci)),), dtype=torch.uint8, device=dy2d.device)
     dw = torch.empty((co, ci), dtype=f32, device=dy2d.device)
@@ -126,7 +140,7 @@ class EffnetTrainFunction(torch.autograd.Function):
             h, cin, cexp, ho = b.hw_in, b.cin, b.cexp, (b.hw_in + b.stride - 1) // b.stride
             x2 = cur.reshape(-1, cin)
             if b.expand != 1:
-                r0 = ops.pointwise(x2, blk._expand_conv.weight.detach().flatten(1).contiguous(), precision="fp32")
+                r0 = pw(ext.precision, x2, blk._expand_conv.weight.detach().flatten(1).contiguous())
                 m0, v0 = bn_train(r0, blk._bn0, ws)
                 a0 = bn_act(r0, m0, v0, blk._bn0.weight.detach(), blk._bn0.bias.detach(), 1)
                 S.update(r0=r0, m0=m0, v0=v0)
@@ -147,8 +161,7 @@ class EffnetTrainFunction(torch.autograd.Function):
             we = blk._se_expand.weight.detach().flatten(1).contiguous()
             _call("mt_se_fc_fwd", pm.data_ptr(), wr.data_ptr(), blk._se_reduce.bias.detach().data_ptr(), we.data_ptr(),
                   blk._se_expand.bias.detach().data_ptr(), gate.data_ptr(), s_pre.data_ptr(), n, cexp, sq, _st())
-            r2_ = ops.pointwise(a1, blk._project_conv.weight.detach().flatten(1).contiguous(), gate=gate, rows_per_gate=ho * ho,
-                                precision="fp32")
+            r2_ = pw(ext.precision, a1, blk._project_conv.weight.detach().flatten(1).contiguous(), gate=gate, rows_per_gate=ho * ho)
             m2, v2 = bn_train(r2_, blk._bn2, ws)
             y = bn_act(r2_, m2, v2, blk._bn2.weight.detach(), blk._bn2.bias.detach(), 0)
             scale = None
@@ -167,7 +180,7 @@ class EffnetTrainFunction(torch.autograd.Function):
             cur = y.view(n, ho, ho, b.cout)
         # ---- head (model.py:286): conv 1x1 320 -> 1280 -> BN -> swish
         x2 = cur.reshape(-1, 320)
-        rh = ops.pointwise(x2, ext._conv_head.weight.detach().flatten(1).contiguous(), precision="fp32")
+        rh = pw(ext.precision, x2, ext._conv_head.weight.detach().flatten(1).contiguous())
         mh, vh = bn_train(rh, ext._bn1, ws)
         feats = bn_act(rh, mh, vh, ext._bn1.weight.detach(), ext._bn1.bias.detach(), 1)
         ctx.ext, ctx.stem, ctx.saved, ctx.head = ext, stem, saved, dict(x=x2, r=rh, m=mh, v=vh)
@@ -201,10 +214,10 @@ class EffnetTrainFunction(torch.autograd.Function):
         d_r, dg, db = bn_act_bwd(dy, hd["r"], hd["m"], hd["v"], ext._bn1.weight.detach(), ext._bn1.bias.detach(), 1, ws)
         G["_bn1.weight"], G["_bn1.bias"] = dg, db
         if req["_conv_head.weight"]:
-            G["_conv_head.weight"] = conv1x1_wgrad(d_r, hd["x"]).view(1280, 320, 1, 1)
+            G["_conv_head.weight"] = conv1x1_wgrad(d_r, hd["x"], ext.precision).view(1280, 320, 1, 1)
         if first >= 18:
             return EffnetTrainFunction._pack(ctx, G)
-        dcur = ops.pointwise(d_r, wT(ext._conv_head.weight), precision="fp32")          # [n*49, 320]
+        dcur = pw(ext.precision, d_r, wT(ext._conv_head.weight))          # [n*49, 320]
         del d_r
         # ---- blocks, last to first
         for b, blk, S in zip(reversed(B0_BLOCKS), reversed(list(ext._blocks)), reversed(ctx.saved)):
@@ -224,9 +237,9 @@ class EffnetTrainFunction(torch.autograd.Function):
             if req[p + "_project_conv.weight"]:
                 xg = torch.empty_like(S["a1"])
                 _call("mt_gate_mul", S["a1"].data_ptr(), S["gate"].data_ptr(), xg.data_ptr(), n, rows_o, cexp, _st())
-                G[p + "_project_conv.weight"] = conv1x1_wgrad(d_r2, xg).view(b.cout, cexp, 1, 1)
+                G[p + "_project_conv.weight"] = conv1x1_wgrad(d_r2, xg, ext.precision).view(b.cout, cexp, 1, 1)
                 del xg
-            dxg = ops.pointwise(d_r2, wT(blk._project_conv.weight), precision="fp32")   # [n*ho*ho, cexp]
+            dxg = pw(ext.precision, d_r2, wT(blk._project_conv.weight))   # [n*ho*ho, cexp]
             del d_r2
             dev = dxg.device
             dgate = torch.empty((n, cexp), dtype=f32, device=dev)
@@ -269,10 +282,10 @@ class EffnetTrainFunction(torch.autograd.Function):
                 G[p + "_bn0.weight"], G[p + "_bn0.bias"] = dg, db
                 del da0
                 if req[p + "_expand_conv.weight"]:
-                    G[p + "_expand_conv.weight"] = conv1x1_wgrad(d_r0, S["inp"].reshape(-1, cin)).view(cexp, cin, 1, 1)
+                    G[p + "_expand_conv.weight"] = conv1x1_wgrad(d_r0, S["inp"].reshape(-1, cin), ext.precision).view(cexp, cin, 1, 1)
                 if not cont:
                     break
-                dcur = ops.pointwise(d_r0, wT(blk._expand_conv.weight), precision="fp32")
+                dcur = pw(ext.precision, d_r0, wT(blk._expand_conv.weight))
                 del d_r0
             else:
                 dcur = da0

@@ -136,10 +136,16 @@ class GraphedTrainStep:
         if sync is not None:
             sync.deferred = self.graph is not None             # inside the capture: record the buckets, exchange later
             sync.buckets = []
-        with torch.no_grad():                                                              # train.py:344-346
+        # frozen extractor (eval, train.py:344-346): no graph of its own; unfrozen (train.py:347-348): its train-mode
+        # autograd node (batch-statistic BatchNorm, drop-connect draws from the graph-safe CUDA generator) is captured too
+        with torch.set_grad_enabled(bool(self.ext.training)):
             x = s["videos"].view(self.b * self.f, 224, 224, 3).permute(0, 3, 1, 2)
             feats = self.ext(x)
             feats = feats.reshape(self.b, self.f, *feats.shape[1:])
+        esync = getattr(self.ext, "_grad_sync", None)
+        if esync is not None:
+            esync.deferred = self.graph is not None
+            esync.buckets = []
         self.model._train_pack = None          # the re-pack of the (just updated) parameters belongs to every step
         y = self.model(feats, mask=s["mask"], size_embedding=s["size_embedding"], identities_mask=s["identities_mask"],
                        positions=s["positions"])
@@ -183,9 +189,10 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture()
         self.graph.replay()
-        sync = getattr(self.model, "_grad_sync", None)
-        if sync is not None:
-            sync.exchange()            # NCCL all-reduce + average of the graph's static gradient buckets
+        for owner in (self.model, self.ext):
+            sync = getattr(owner, "_grad_sync", None)
+            if sync is not None:
+                sync.exchange()        # NCCL all-reduce + average of the graph's static gradient buckets
         if not self.capture_optimizer:
             self.opt.step()            # eager, on the graph's static .grad tensors: schedulers / any optimizer work
         return self.loss

@@ -620,3 +620,85 @@ def test_features_gradient_reaches_the_extractor():
     torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw]))(ol, labels).backward()
     assert fx.grad is not None and fx.grad.shape == feats.shape
     assert rel_err(fx.grad.cpu(), fo.grad) <= 2e-3
+
+
+def test_graphed_train_step_with_an_unfrozen_extractor_matches_eager_steps():
+    """train.py:155-170 under GraphedTrainStep: the extractor's train-mode autograd node (batch-statistic BatchNorm, running
+    statistics, the last blocks unfrozen) is captured with the rest of the step.  Drop-connect off (rate 0) so that the eager
+    loop and the replays see the same arithmetic; same losses, parameters and running statistics after the same steps."""
+    from mintime_b200 import EfficientNet, synth
+    from mintime_b200.graphed import GraphedTrainStep
+    case = "b2_f8_id2"
+    cfg, tsd, meta, _, labels, pw = grad_case_inputs(case)
+    cfg["model"]["depth"] = 2
+    tsd = synth.make_tsf_state_dict(cfg, 777)
+    B, f = 2, 8
+    frames = synth.make_frames(B, f, seed=9, mask=meta["mask"], dtype=torch.uint8).to(DEV)
+    lossf = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([pw], device=DEV))
+
+    def make():
+        ext = EfficientNet.from_name("efficientnet-b0", precision="bf16", drop_connect_rate=0.0)
+        ext.load_state_dict(synth.make_effnet_state_dict(1234, conditioned=True))
+        ext = ext.to(DEV).train()
+        for name, p in ext.named_parameters():                # --extractor_unfreeze_blocks 2 (train.py:157-167)
+            if name.startswith("_blocks."):
+                p.requires_grad_(int(name.split(".")[1]) >= 14)
+            else:
+                p.requires_grad_(name.startswith(("_conv_head", "_bn1")))
+        m = SizeInvariantTimeSformer(config=cfg, precision="bf16")
+        m.load_state_dict(tsd)
+        m = m.to(DEV).train()
+        params = list(m.parameters()) + [p for p in ext.parameters() if p.requires_grad]
+        return ext, m, torch.optim.SGD(params, lr=0.01, weight_decay=1e-4)
+
+    ext, model, opt = make()
+    eager = []
+    for it in range(4):
+        feats = ext(frames.view(B * f, 224, 224, 3).permute(0, 3, 1, 2)).reshape(B, f, 1280, 7, 7)
+        opt.zero_grad(set_to_none=True)
+        y = model(feats, mask=meta["mask"].to(DEV), size_embedding=meta["size_embedding"],
+                  identities_mask=meta["identities_mask"].to(DEV), positions=meta["positions"].to(DEV))
+        loss = lossf(y, labels.to(DEV))
+        loss.backward()
+        opt.step()
+        eager.append(loss.item())
+    ext2, model2, opt2 = make()
+    gs = GraphedTrainStep(ext2, model2, opt2, lossf, B, f, frame_dtype=torch.uint8, device=DEV, warmup=2)
+    gs.static["videos"].copy_(frames)
+    for k in ("mask", "identities_mask", "size_embedding", "positions"):
+        gs.static[k].copy_(meta[k])
+    gs.static["labels"].copy_(labels)
+    gs.capture()
+    got = [gs.replay().item() for _ in range(2)]
+    assert np.allclose(got, eager[2:], rtol=0, atol=3e-3), (got, eager)
+    assert rel_err(ext2._conv_head.weight, ext._conv_head.weight) <= 2e-3
+    assert rel_err(ext2._blocks[15]._depthwise_conv.weight, ext._blocks[15]._depthwise_conv.weight) <= 2e-3
+    assert rel_err(ext2._bn1.running_var, ext._bn1.running_var) <= 2e-3          # 4 momentum updates on both sides
+    assert torch.equal(ext2._blocks[3]._bn1.weight, ext._blocks[3]._bn1.weight)  # frozen blocks did not move
+
+
+def test_extractor_train_mode_bf16_gemms_track_the_fp32_path():
+    """precision="bf16" in train mode = mixed precision: the 1x1 convolutions (forward, data and weight gradients) on the
+    tensor cores with bf16 operands, everything else fp32.  Same input, conditioned weights, no drop-connect: the features
+    and the gradients stay close to the exact fp32 path (stated bars: features rel-L2 5e-2 -- batch statistics over only 4
+    faces re-normalise the bf16 rounding noise of 50 layers -- gradient cosine 0.97, as for the transformer's bf16 backward)."""
+    from mintime_b200 import EfficientNet, synth
+    esd = synth.make_effnet_state_dict(1234, conditioned=True)
+    meta = synth.make_batch_meta(1, 4, [1], seed=11, pad_tail=False)
+    x = synth.make_frames(1, 4, seed=11, mask=meta["mask"]).view(4, 224, 224, 3).permute(0, 3, 1, 2).to(DEV)
+    probe = torch.randn((4, 1280, 7, 7), generator=torch.Generator().manual_seed(3)).to(DEV)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        ext = EfficientNet.from_name("efficientnet-b0", precision=prec, drop_connect_rate=0.0)
+        ext.load_state_dict(esd)
+        ext = ext.to(DEV).train()
+        y = ext(x)
+        (y.float() * probe).sum().backward()
+        res[prec] = (y.detach().float(), {k: p.grad.detach().clone() for k, p in ext.named_parameters() if p.grad is not None})
+    torch.cuda.synchronize()
+    assert rel_err(res["bf16"][0], res["fp32"][0]) <= 5e-2
+    for k in ("_conv_head.weight", "_blocks.15._project_conv.weight", "_blocks.12._expand_conv.weight", "_blocks.5._bn1.bias",
+              "_blocks.1._expand_conv.weight", "_conv_stem.weight"):
+        a, b = res["bf16"][1][k].double().flatten(), res["fp32"][1][k].double().flatten()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        assert cos >= 0.97, (k, cos)
