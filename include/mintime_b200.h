@@ -352,7 +352,7 @@ int mt_grad_prep(int precision, const void* src, int src_is_f32, void* out_rm, v
 int mt_linear_wgrad(int precision, const void* dy_t, const void* x_t, float* dw, int n_out, int k_in, int mp, void* stream);
 
 /* The same weight gradient straight from the row-major operands: dw f32 [n_out][k_in] += dy [m][n_out]^T * x [m][k_in]
- * (bf16 only; n_out, k_in multiples of 64; any m).  Both operands enter tcgen05.mma MN-major (the contraction index is
+ * (bf16 only; n_out, k_in multiples of 8; any m).  Both operands enter tcgen05.mma MN-major (the contraction index is
  * the slow one in memory), so no transposed copies (mt_grad_prep out_t) are needed: the backward of
  * size_invariant_timesformer.py:109-144 / :65-76 w.r.t. to_qkv / to_out / net.0 / net.3 weights. */
 int mt_linear_wgrad_nt(int precision, const void* dy, const void* x, float* dw, int n_out, int k_in, int m, void* stream);

@@ -788,6 +788,7 @@ int launch_tc_impl(const GemmArgs& g, cudaStream_t stream) {
     // several column tiles: a TMA store box is 128 B wide, so tiles must start on 64-column boundaries
     // (a partial last box of tile i would otherwise spill stale staging data into tile i+1's columns)
     if (parts > 1) bn = (bn + 63) / 64 * 64;
+    if (g.mn_major) bn = (bn + 63) / 64 * 64;         // MN-major operands: whole 64-channel atoms per tile (TMA zero-fills beyond N)
   }
   p.block_n = bn;
   p.tiles_m = (g.M + kBlockM - 1) / kBlockM;

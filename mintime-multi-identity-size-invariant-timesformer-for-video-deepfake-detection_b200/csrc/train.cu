@@ -772,8 +772,8 @@ extern "C" int mt_linear_wgrad(int precision, const void* dy_t, const void* x_t,
 extern "C" int mt_linear_wgrad_nt(int precision, const void* dy, const void* x, float* dw, int n_out, int k_in, int m,
                                   void* stream) {
   MT_REQUIRE(dy && x && dw && n_out > 0 && k_in > 0 && m > 0, "linear_wgrad_nt: bad argument");
-  MT_REQUIRE(precision == MT_PREC_BF16 && n_out % 64 == 0 && k_in % 64 == 0,
-             "linear_wgrad_nt: bf16 only, n_out (%d) and k_in (%d) multiples of 64", n_out, k_in);
+  MT_REQUIRE(precision == MT_PREC_BF16 && n_out % 8 == 0 && k_in % 8 == 0,
+             "linear_wgrad_nt: bf16 only, n_out (%d) and k_in (%d) multiples of 8", n_out, k_in);
   GemmArgs g{};
   g.a = dy; g.w = x; g.M = n_out; g.N = k_in; g.K = m;
   g.mn_major = 1;

@@ -92,11 +92,10 @@ def pw(precision, x2d, w2d, **kw):
 
 
 def conv1x1_wgrad(dy2d, a2d, precision="fp32"):
-    """dW [cout, cin] = dy^T a  (both [rows, *] fp32); bf16 mode: channel counts that are multiples of 64 (the 192 / 320 /
-    1152 / 1280-wide layers, most of the FLOPs) go through the MN-major tensor-core weight gradient"""
+    """dW [cout, cin] = dy^T a  (both [rows, *] fp32); bf16 mode: the MN-major tensor-core weight gradient on bf16 copies"""
     rows, co = dy2d.shape
     ci = a2d.shape[1]
-    if precision == "bf16" and co % 64 == 0 and ci % 64 == 0:
+    if precision == "bf16" and co % 8 == 0 and ci % 8 == 0:
         dw = torch.zeros((co, ci), dtype=f32, device=dy2d.device)
         return ops.linear_wgrad_nt_(dw, dy2d.bfloat16(), a2d.bfloat16())
     lib = _lib.load()

@@ -406,7 +406,7 @@ def linear_wgrad_(dw, dy_t, x_t, precision="bf16"):
 
 def linear_wgrad_nt_(dw, dy, x):
     """dw (float32 [n_out, k_in], in place) += dy [m, n_out].T @ x [m, k_in], bf16 row-major operands as they are
-    (MN-major tcgen05 operands: no transposed copies); n_out and k_in multiples of 64"""
+    (MN-major tcgen05 operands: no transposed copies); n_out and k_in multiples of 8"""
     _prep(dy, torch.bfloat16); _prep(x, torch.bfloat16); _prep(dw, torch.float32)
     m, n_out = dy.shape
     k_in = x.shape[1]

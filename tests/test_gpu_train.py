@@ -74,7 +74,8 @@ def test_linear_wgrad_split_k(prec, n_out, k_in, m):
 
 
 @pytest.mark.parametrize("n_out,k_in,m", [(512, 512, 785 * 3), (1536, 512, 4000), (4096, 512, 1570), (512, 2048, 25120),
-                                          (128, 64, 100), (192, 320, 777)])
+                                          (128, 64, 100), (192, 320, 777), (96, 16, 5000), (672, 112, 3000), (40, 240, 777),
+                                          (1280, 320, 6272)])
 def test_linear_wgrad_from_row_major_operands(n_out, k_in, m):
     """dW += dY^T X with dY [m][n_out] and X [m][k_in] as they lie in memory (MN-major tcgen05 operands, TMA zero fill for
     the ragged token tail): equals the transposed-copy route and the fp64 product."""
