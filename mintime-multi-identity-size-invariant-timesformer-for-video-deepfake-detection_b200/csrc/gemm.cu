@@ -6,11 +6,13 @@
 //      warp 0      TMA producer: A (128 x 64) and W (block_n x 64) tiles, 128-byte swizzle, mbarrier ring
 //      warp 1      MMA issuer: tcgen05.mma kind::f16, fp32 accumulators in TMEM, double buffered
 //      warps 2-5   epilogue: tcgen05.ld -> bias / swish / GEGLU in registers -> swizzled smem staging ->
-//                  TMA store (bf16) or TMA reduce-add (fp32 residual stream), double buffered, so global
-//                  writes are full 128-byte lines issued by the copy engine instead of per-row stores
-//      warps 6-9   (GATED only) scale the landed A tile by the squeeze-excite gate before the MMA reads it
-//    The direct-store epilogue (TMA_OUT = false) is kept for the two cases that need per-row gathers:
-//    the MBConv skip connection and the patch-embedding (+pos/size embedding rows).
+//      (2-9 for    TMA store (bf16) or TMA reduce-add (fp32 residual stream), double buffered, so global
+//       bf16       writes are full 128-byte lines issued by the copy engine instead of per-row stores; the
+//       stores)    8-warp bf16 form has no block-wide barrier (per-warp slabs, straight-line 32 x 32 units)
+//      last 4      (GATED only) scale the landed A tile by the squeeze-excite gate (bf16, HMUL2) before the MMA reads it
+//    Operands are K-major (A [M][K], W [N][K]); mn_major = 1 takes both with the contraction index slow ([K][M], [K][N]:
+//    the weight gradient dW = dY^T X straight from the row-major tensors).  The direct-store epilogue (TMA_OUT = false)
+//    is kept for the patch-embedding (+pos/size embedding rows) and for outputs whose pitch TMA cannot address.
 //  * gemm_simt_kernel (fp32 / any T): plain FFMA tiles with the same epilogues -- the exact path.
 #include <cuda.h>
 #include <cudaTypedefs.h>

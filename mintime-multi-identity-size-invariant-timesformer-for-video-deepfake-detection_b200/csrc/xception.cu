@@ -282,7 +282,6 @@ int xc_forward(const mt_xception_weights_t* w, const void* x, int x_dtype, void*
         MT_LAUNCH_CHECK("xc_dw3x3_kernel");
       }
       T* pwo = (dwo == t0) ? t1 : t0;
-      if (pwo == cur) return MT_ERR_ARG;   // (cannot happen: cur is never t0/t1 while a block runs)
       // identity-skip blocks add their input in the last unit's epilogue (xception.py:73-75)
       const bool last = r == bk.reps - 1;
       const void* resid = (last && bk.stride == 1 && bk.cin == bk.cout) ? cur : nullptr;
