@@ -262,9 +262,11 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__
   const int c = blockIdx.x * 32 + cl;
   const long long npos = (long long)n * Ho * Ho;
   const long long p0 = (long long)blockIdx.y * pos_per_block, p1 = min(npos, p0 + pos_per_block);
-  double acc[K * K];
+  // fp32 inside a thread's share of the chunk (a few hundred positions), fp64 across threads and chunks: the double-precision
+  // converts and FMAs per tap made this kernel 8 ms of the unfrozen step
+  float acc[K * K];
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) acc[t] = 0.0;
+  for (int t = 0; t < K * K; ++t) acc[t] = 0.f;
   if (c < C) {
     for (long long p = p0 + rl; p < p1; p += kRedRows) {
       const unsigned pp = (unsigned)p;                      // (npos < 2^31: 32-bit divisions)
@@ -278,14 +280,14 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__
         for (int kx = 0; kx < K; ++kx) {
           const int ix = ox * S + kx - pad;
           if (ix < 0 || ix >= H) continue;
-          acc[ky * K + kx] += (double)g * (double)in[(((size_t)img * H + iy) * H + ix) * C + c];
+          acc[ky * K + kx] = fmaf(g, in[(((size_t)img * H + iy) * H + ix) * C + c], acc[ky * K + kx]);
         }
       }
     }
   }
   for (int t = 0; t < K * K; ++t) {
     __syncthreads();
-    red[rl][cl] = acc[t];
+    red[rl][cl] = (double)acc[t];
     __syncthreads();
     if (rl == 0 && c < C) {
       double s = red[0][cl];
