@@ -40,6 +40,9 @@ struct ProfScope {
   cudaStream_t st;
 };
 
+// effnet.cu: plain 3x3 s1 p1 depthwise convolution (bf16 NHWC, optional ReLU on the input) on the TMA-staged FFMA2 kernel
+int launch_dw_plain_bf16(const void* in, const float* w, void* out, int n_img, int H, int C, int relu_in, cudaStream_t st);
+
 #define MT_LAUNCH_CHECK(what)                                   \
   do {                                                          \
     cudaError_t e__ = cudaGetLastError();                       \

@@ -129,9 +129,12 @@ __device__ __forceinline__ float2 silu2(float2 x, float2 hsh) {
 // One R x 7 patch of outputs for one channel pair.  `tp` points at the channel pair's word of the patch's
 // top-left INPUT pixel inside the shared-memory tile ([IH][IW][CW] bf16); pstride / rstride are the
 // pixel / row pitches in bytes.
-template <int K, int S, int R>
+// MODE 0: the MBConv depthwise (BN shift + swish + squeeze-excite pool sums).  MODE 1: a plain depthwise convolution (no shift,
+// no activation, no pool) with an optional ReLU folded into the loads -- SeparableConv2d.conv1 of the Xception extractor
+// (reference models/xception.py:20 behind the ReLUs of :43-58).
+template <int K, int S, int R, int MODE = 0>
 __device__ __forceinline__ void dw_patch(const uint8_t* tp, const int pstride, const int rstride,
-                                         const float2 (&wv)[K * K], float2 (&acc)[R][kDwSX]) {
+                                         const float2 (&wv)[K * K], float2 (&acc)[R][kDwSX], const bool relu_in = false) {
   constexpr int SX = kDwSX, NIN = (SX - 1) * S + K, NROW = (R - 1) * S + K;
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -142,7 +145,10 @@ __device__ __forceinline__ void dw_patch(const uint8_t* tp, const int pstride, c
     float2 row[NIN];
     const uint8_t* rp = tp + ir * rstride;
 #pragma unroll
-    for (int jj = 0; jj < NIN; ++jj) row[jj] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(rp + jj * pstride));
+    for (int jj = 0; jj < NIN; ++jj) {
+      row[jj] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(rp + jj * pstride));
+      if (MODE == 1 && relu_in) { row[jj].x = fmaxf(row[jj].x, 0.f); row[jj].y = fmaxf(row[jj].y, 0.f); }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int ky = ir - r * S;                 // compile-time after unrolling
@@ -158,18 +164,18 @@ __device__ __forceinline__ void dw_patch(const uint8_t* tp, const int pstride, c
 // All R x 7 patches of one tile that belong to this thread's (channel pair, slot): stencil, BN shift + swish,
 // bf16 store, and the thread's share of the squeeze-excite pool sum.  `tile` points at the channel pair's word
 // of the tile's first input pixel.
-template <int K, int S>
+template <int K, int S, int MODE = 0>
 __device__ __forceinline__ float2 dw_tile(const uint8_t* tile, const int pstride, const int rstride,
                                           const float2 (&wv)[K * K], const float2 hsh, bf16* __restrict__ out, int img,
                                           int oy_t, int ox_t, int oy_end, int ox_end, int Ho, int Wo, int C, int c,
-                                          int slot, int n_strips, int strips_x, int NS) {
+                                          int slot, int n_strips, int strips_x, int NS, const bool relu_in = false) {
   constexpr int R = dw_simt_rows(K, S), SX = kDwSX;
   float2 psum = make_float2(0.f, 0.f);
   for (int strip = slot; strip < n_strips; strip += NS) {
     const int sy = strip / strips_x, sx = strip - sy * strips_x;
     const int oy0 = sy * R, ox0 = sx * SX;
     float2 acc[R][SX];
-    dw_patch<K, S, R>(tile + (oy0 * S) * rstride + (ox0 * S) * pstride, pstride, rstride, wv, acc);
+    dw_patch<K, S, R, MODE>(tile + (oy0 * S) * rstride + (ox0 * S) * pstride, pstride, rstride, wv, acc, relu_in);
     // outputs: one bf16x2 word per pixel; whole patches (the common case) take the branch-free path
     uint8_t* op = reinterpret_cast<uint8_t*>(out + (((size_t)img * Ho + oy_t + oy0) * Wo + ox_t + ox0) * C + c);
     const size_t cbytes = (size_t)C * 2, rbytes = (size_t)Wo * cbytes;
@@ -179,8 +185,8 @@ __device__ __forceinline__ float2 dw_tile(const uint8_t* tile, const int pstride
         uint8_t* p = op + r * rbytes;
 #pragma unroll
         for (int j = 0; j < SX; ++j) {
-          const float2 v = silu2(acc[r][j], hsh);
-          psum = __fadd2_rn(psum, v);
+          const float2 v = MODE == 1 ? acc[r][j] : silu2(acc[r][j], hsh);
+          if (MODE == 0) psum = __fadd2_rn(psum, v);
           *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v.x, v.y);
           p += cbytes;
         }
@@ -191,8 +197,8 @@ __device__ __forceinline__ float2 dw_tile(const uint8_t* tile, const int pstride
 #pragma unroll
         for (int j = 0; j < SX; ++j) {
           if (oy0 + r < oy_end && ox0 + j < ox_end) {
-            const float2 v = silu2(acc[r][j], hsh);
-            psum = __fadd2_rn(psum, v);
+            const float2 v = MODE == 1 ? acc[r][j] : silu2(acc[r][j], hsh);
+            if (MODE == 0) psum = __fadd2_rn(psum, v);
             *reinterpret_cast<uint32_t*>(op + r * rbytes + j * cbytes) = pack_bf16x2(v.x, v.y);
           }
         }
@@ -202,11 +208,11 @@ __device__ __forceinline__ float2 dw_tile(const uint8_t* tile, const int pstride
   return psum;
 }
 
-template <int K, int S, int CWT>   // CWT: channels per chunk at compile time (0 = read g.CW)
+template <int K, int S, int CWT, int MODE = 0>   // CWT: channels per chunk at compile time (0 = read g.CW)
 __global__ void __launch_bounds__(256, 2)
 dwconv_simt_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict__ w,
                    const float* __restrict__ shift, bf16* __restrict__ out, float* __restrict__ pool_part, int n_img,
-                   int Ho, int Wo, int C, int pad_lo, DwSimtGeom g) {
+                   int Ho, int Wo, int C, int pad_lo, DwSimtGeom g, int relu_in) {
   extern __shared__ __align__(128) uint8_t dsm_raw[];
   uint8_t* ring = dsm_raw + ((128u - (ptx::smem_u32(dsm_raw) & 127u)) & 127u);   // stays a shared-space pointer
   float2* red = reinterpret_cast<float2*>(ring + 2 * g.tile_stride);   // [2][threads]
@@ -241,8 +247,11 @@ dwconv_simt_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
   float2 wv[K * K];
 #pragma unroll
   for (int t = 0; t < K * K; ++t) wv[t] = *reinterpret_cast<const float2*>(w + (size_t)t * C + c);
-  float2 hsh = *reinterpret_cast<const float2*>(shift + c);   // BN shift, pre-halved for silu2
-  hsh.x *= 0.5f; hsh.y *= 0.5f;
+  float2 hsh = make_float2(0.f, 0.f);
+  if (MODE == 0) {
+    hsh = *reinterpret_cast<const float2*>(shift + c);        // BN shift, pre-halved for silu2
+    hsh.x *= 0.5f; hsh.y *= 0.5f;
+  }
   const int pstride = CW * 2, rstride = g.IW * pstride;
   __syncthreads();                                // barriers initialised
 
@@ -256,12 +265,12 @@ dwconv_simt_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
     const uint8_t* tile = ring + (step & 1) * g.tile_stride + cp * 4;
     const int oy_t = ty * g.TH, ox_t = tx * g.TW;
     const int oy_end = min(g.TH, Ho - oy_t), ox_end = min(g.TW, Wo - ox_t);   // valid outputs of this tile
-    const float2 psum = dw_tile<K, S>(tile, pstride, rstride, wv, hsh, out, img, oy_t, ox_t, oy_end, ox_end, Ho, Wo, C, c,
-                                      slot, g.n_strips, g.strips_x, g.NS);
+    const float2 psum = dw_tile<K, S, MODE>(tile, pstride, rstride, wv, hsh, out, img, oy_t, ox_t, oy_end, ox_end, Ho, Wo, C, c,
+                                            slot, g.n_strips, g.strips_x, g.NS, relu_in != 0);
     float2* rb = red + (step & 1) * g.threads;
-    rb[tid] = psum;
+    if (MODE == 0) rb[tid] = psum;
     __syncthreads();                              // tile consumed (ring slot free) + partial sums visible
-    if (slot == 0) {
+    if (MODE == 0 && slot == 0) {
       float2 s = rb[cp];
       for (int sl = 1; sl < g.NS; ++sl) { const float2 v = rb[sl * CP + cp]; s.x += v.x; s.y += v.y; }
       *reinterpret_cast<float2*>(pool_part + ((size_t)img * g.tiles + t) * C + c) = s;   // one writer per entry

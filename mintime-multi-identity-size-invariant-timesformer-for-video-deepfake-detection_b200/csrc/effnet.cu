@@ -555,14 +555,14 @@ int launch_dw_t(const void* in, const float* w, const float* shift, void* out, f
 
 int device_sms() { return current_sms(); }
 
-template <int K, int S>
+template <int K, int S, int MODE = 0>
 int launch_dw_simt_ks(const CUtensorMap& tm, const float* w, const float* shift, bf16* o, float* pool, int n_img, int H,
-                      int C, const DwSimtGeom& g, cudaStream_t st) {
+                      int C, const DwSimtGeom& g, cudaStream_t st, int relu_in = 0) {
   const int Ho = (H + S - 1) / S;
-  using Kern = void (*)(const CUtensorMap, const float*, const float*, bf16*, float*, int, int, int, int, int, DwSimtGeom);
+  using Kern = void (*)(const CUtensorMap, const float*, const float*, bf16*, float*, int, int, int, int, int, DwSimtGeom, int);
   const int slot = g.CW == 32 ? 1 : (g.CW == 48 ? 2 : (g.CW == 64 ? 3 : 0));
-  static const Kern kerns[4] = {dwconv_simt_kernel<K, S, 0>, dwconv_simt_kernel<K, S, 32>, dwconv_simt_kernel<K, S, 48>,
-                                dwconv_simt_kernel<K, S, 64>};
+  static const Kern kerns[4] = {dwconv_simt_kernel<K, S, 0, MODE>, dwconv_simt_kernel<K, S, 32, MODE>,
+                                dwconv_simt_kernel<K, S, 48, MODE>, dwconv_simt_kernel<K, S, 64, MODE>};
   Kern kern = kerns[slot];
   if (first_use_on_device(reinterpret_cast<const void*>(kern))) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
@@ -577,7 +577,7 @@ int launch_dw_simt_ks(const CUtensorMap& tm, const float* w, const float* shift,
   const long long work = (long long)n_img * g.tiles;
   const int workers = (int)std::max(1LL, std::min(work, (long long)(device_sms() * per_sm) / g.n_cchunks));
   dim3 grid(workers, g.n_cchunks);
-  kern<<<grid, g.threads, g.smem, st>>>(tm, w, shift, o, pool, n_img, Ho, Ho, C, same_pad_lo(H, K, S), g);
+  kern<<<grid, g.threads, g.smem, st>>>(tm, w, shift, o, pool, n_img, Ho, Ho, C, same_pad_lo(H, K, S), g, relu_in);
   MT_LAUNCH_CHECK("dwconv_simt_kernel");
   return MT_OK;
 }
@@ -602,6 +602,25 @@ int launch_dw_simt(const void* in, const float* w, const float* shift, void* out
   if (k == 5 && s == 1) return launch_dw_simt_ks<5, 1>(tm, w, shift, o, pool, n_img, H, C, g, st);
   return launch_dw_simt_ks<5, 2>(tm, w, shift, o, pool, n_img, H, C, g, st);
 }
+
+}  // namespace
+
+// Plain 3x3 / pad 1 / stride 1 depthwise convolution on the same kernel (MODE 1: no shift, no activation, no pool sums; optional
+// ReLU on the input): SeparableConv2d.conv1 of the Xception extractor, bf16 NHWC.  w: f32 [9][C] tap-major.
+int launch_dw_plain_bf16(const void* in, const float* w, void* out, int n_img, int H, int C, int relu_in, cudaStream_t st) {
+  DwSimtGeom g;
+  if (!dw_simt_geom(&g, H, H, C, 3, 1, n_img, device_sms())) {
+    set_error("dwconv(plain): no tile fits for h=%d c=%d", H, C);
+    return MT_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tm;
+  int rc = make_tmap_nhwc_bf16_plain(&tm, in, n_img, H, H, C, g.CW, g.IW, g.IH);
+  if (rc) return rc;
+  ProfScope prof(st, 18.0 * (double)n_img * H * H * C, (double)n_img * C * (double)H * H * 4, "xc_dw3x3 C%d H%d", C, H);
+  return launch_dw_simt_ks<3, 1, 1>(tm, w, nullptr, reinterpret_cast<bf16*>(out), nullptr, n_img, H, C, g, st, relu_in);
+}
+
+namespace {
 
 bool dw_simt_ok(int h, int w_, int c, int k, int s) { return h == w_ && (k == 3 || k == 5) && (s == 1 || s == 2); }
 

@@ -6,7 +6,9 @@
 // dense 3x3 stem convolutions run on the library's GEMM (mt_pointwise_fwd: tcgen05 on the bf16 path) with the following
 // BatchNorm folded into the weight rows and the shift.  What this file adds are the memory-bound pieces around them:
 //   * im2col of a 3x3 VALID convolution (xception.py:105,109: conv1 stride 2, conv2 stride 1, padding 0)
-//   * depthwise 3x3, padding 1, no bias (SeparableConv2d.conv1, xception.py:20) with the preceding ReLU folded into its loads
+//   * depthwise 3x3, padding 1, no bias (SeparableConv2d.conv1, xception.py:20) with the preceding ReLU folded into its loads:
+//     bf16 on the MBConv stack's TMA-staged FFMA2 kernel (dwconv_simt.cuh MODE 1, via launch_dw_plain_bf16), fp32 on the simple
+//     kernel below
 //   * MaxPool2d(3, 2, 1) (xception.py:63)
 //   * the stride-2 pixel gather in front of a skip projection (xception.py:35)
 // ReLUs never run as kernels: each one sits in front of exactly one consumer (a depthwise conv, the im2col of conv2, or
@@ -166,9 +168,29 @@ __global__ void __launch_bounds__(256) xc_im2col3x3_c8_kernel(const T* __restric
   }
 }
 
+inline unsigned grid_for(size_t total);
+
+// depthwise 3x3 of one separable convolution: bf16 on the TMA-staged FFMA2 kernel of the MBConv stack (effnet.cu, MODE 1),
+// fp32 (exact path) on the simple kernel above
+template <typename T>
+int xc_dw(const T* in, const float* w, T* out, int n, int h, int c, int relu_in, cudaStream_t st);
+
 inline unsigned grid_for(size_t total) {
   const size_t blocks = (total + 255) / 256;
   return (unsigned)std::min<size_t>(blocks, (size_t)current_sms() * 32);
+}
+
+template <>
+int xc_dw<bf16>(const bf16* in, const float* w, bf16* out, int n, int h, int c, int relu_in, cudaStream_t st) {
+  return launch_dw_plain_bf16(in, w, out, n, h, c, relu_in, st);
+}
+template <>
+int xc_dw<float>(const float* in, const float* w, float* out, int n, int h, int c, int relu_in, cudaStream_t st) {
+  const size_t total = (size_t)n * h * h * (c / 8);
+  ProfScope ps(st, 18.0 * (double)n * h * h * c, 2.0 * (double)n * h * h * c * 4.0, "xc_dw3x3 C%d H%d", c, h);
+  xc_dw3x3_kernel<float><<<grid_for(total), 256, 0, st>>>(in, w, out, n, h, h, c, relu_in);
+  MT_LAUNCH_CHECK("xc_dw3x3_kernel");
+  return MT_OK;
 }
 
 // geometry of the network at a given input size (224 in MINTIME): xception.py:105-131
@@ -275,12 +297,8 @@ int xc_forward(const mt_xception_weights_t* w, const void* x, int x_dtype, void*
       const int relu_in = (b == 1) ? 1 : ((r == 0) ? bk.relu0 : 1);   // block 1: its input is relu(bn2(.)) (xception.py:154)
       const mt_xc_sep_t& u = w->sep[unit];
       T* dwo = (src == t0) ? t1 : t0;
-      const size_t total = (size_t)rows_in * (ch / 8);
-      {
-        ProfScope ps(st, 18.0 * rows_in * ch, 2.0 * rows_in * ch * (double)sizeof(T), "xc_dw3x3 C%d H%d", ch, hin);
-        xc_dw3x3_kernel<T><<<grid_for(total), 256, 0, st>>>(src, u.dw_w, dwo, n, hin, hin, ch, relu_in);
-        MT_LAUNCH_CHECK("xc_dw3x3_kernel");
-      }
+      rc = xc_dw<T>(src, u.dw_w, dwo, n, hin, ch, relu_in, st);
+      if (rc) return rc;
       T* pwo = (dwo == t0) ? t1 : t0;
       // identity-skip blocks add their input in the last unit's epilogue (xception.py:73-75)
       const bool last = r == bk.reps - 1;
@@ -326,12 +344,12 @@ int xc_forward(const mt_xception_weights_t* w, const void* x, int x_dtype, void*
     const int hh = g.hb[12], rows = n * hh * hh;
     const mt_xc_sep_t& u3 = w->sep[unit];
     const mt_xc_sep_t& u4 = w->sep[unit + 1];
-    xc_dw3x3_kernel<T><<<grid_for((size_t)rows * 128), 256, 0, st>>>(cur, u3.dw_w, t0, n, hh, hh, 1024, 0);
-    MT_LAUNCH_CHECK("xc_dw3x3_kernel(conv3)");
+    rc = xc_dw<T>(cur, u3.dw_w, t0, n, hh, 1024, 0, st);
+    if (rc) return rc;
     rc = mt_pointwise_fwd(precision, t0, u3.pw.w, u3.pw.shift, nullptr, 0, nullptr, 0, t1, rows, 1536, 1024, stream);
     if (rc) return rc;
-    xc_dw3x3_kernel<T><<<grid_for((size_t)rows * 192), 256, 0, st>>>(t1, u4.dw_w, t0, n, hh, hh, 1536, 1);
-    MT_LAUNCH_CHECK("xc_dw3x3_kernel(conv4)");
+    rc = xc_dw<T>(t1, u4.dw_w, t0, n, hh, 1536, 1, st);
+    if (rc) return rc;
     rc = mt_pointwise_fwd(precision, t0, u4.pw.w, u4.pw.shift, nullptr, 0, nullptr, 0, feats, rows, 2048, 1536, stream);
     if (rc) return rc;
   }
