@@ -268,8 +268,16 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const T* __restrict__ h,
   float u[8], g[8];
   load8(h + row * 2 * hd + hc, u);
   load8(h + row * 2 * hd + hc + 32, g);
+  if (sizeof(T) == 4) {                       // exact path: erff
 #pragma unroll
-  for (int i = 0; i < 8; ++i) u[i] *= gelu_erf(g[i]);
+    for (int i = 0; i < 8; ++i) u[i] *= gelu_erf(g[i]);
+  } else {                                    // bf16 path: the packed form of the fused GEMM epilogue (inference) -- one arithmetic
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 r = geglu2(make_float2(u[2 * i], u[2 * i + 1]), make_float2(g[2 * i], g[2 * i + 1]));
+      u[2 * i] = r.x; u[2 * i + 1] = r.y;
+    }
+  }
   store8(out + row * hd + oc, u);
 }
 
