@@ -115,6 +115,31 @@ __device__ __forceinline__ float2 geglu2(float2 u, float2 g) {
   return __fmul2_rn(u, __ffma2_rn(h, erf2, h));                                  // u * 0.5 g (1 + erf)
 }
 
+// Packed derivative pieces of GELU for the GEGLU backward (bf16 path): cdf = Phi(g) = (1 + erf(g / sqrt 2)) / 2 and
+// pdf = phi(g) = exp(-g^2 / 2) / sqrt(2 pi) from ONE evaluation of the same Abramowitz-Stegun erf as geglu2 -- its exponential
+// exp(-z^2), z = g / sqrt 2, is exp(-g^2 / 2).
+__device__ __forceinline__ void gelu_cdf_pdf2(float2 g, float2& cdf, float2& pdf) {
+  const float2 z = __fmul2_rn(g, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 den = __ffma2_rn(az, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  float2 p = __ffma2_rn(make_float2(-1.061405429f, -1.061405429f), t, make_float2(1.453152027f, 1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(-1.421413741f, -1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(0.284496736f, 0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(-0.254829592f, -0.254829592f));
+  const float2 npt = __fmul2_rn(p, t);
+  const float2 q = __fmul2_rn(__fmul2_rn(az, make_float2(-1.4426950408889634f, -1.4426950408889634f)), az);
+  float2 ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(q.y));
+  const float2 r = __ffma2_rn(npt, ex, make_float2(1.0f, 1.0f));                 // erf(|z|)
+  const float2 erf2 = make_float2(copysignf(r.x, z.x), copysignf(r.y, z.y));
+  cdf = __ffma2_rn(erf2, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  pdf = __fmul2_rn(ex, make_float2(0.39894228040143268f, 0.39894228040143268f));
+}
+
 // 8 consecutive elements <-> registers
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);

@@ -294,14 +294,28 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const T* __restrict__ h,
   load8(h + row * 2 * hd + hc, u);
   load8(h + row * 2 * hd + hc + 32, g);
   load8(dout + row * hd + oc, d);
+  if (sizeof(T) == 4) {                       // exact path
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float cdf = 0.5f * (1.0f + erff(g[i] * 0.70710678118654752f));
-    const float pdf = 0.39894228040143268f * expf(-0.5f * g[i] * g[i]);
-    const float du = d[i] * g[i] * cdf;
-    const float dg = d[i] * u[i] * fmaf(g[i], pdf, cdf);
-    u[i] = du;
-    g[i] = dg;
+    for (int i = 0; i < 8; ++i) {
+      const float cdf = 0.5f * (1.0f + erff(g[i] * 0.70710678118654752f));
+      const float pdf = 0.39894228040143268f * expf(-0.5f * g[i] * g[i]);
+      const float du = d[i] * g[i] * cdf;
+      const float dg = d[i] * u[i] * fmaf(g[i], pdf, cdf);
+      u[i] = du;
+      g[i] = dg;
+    }
+  } else {                                    // bf16 path: packed math, one erf evaluation for cdf and pdf
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 g2 = make_float2(g[2 * i], g[2 * i + 1]), u2 = make_float2(u[2 * i], u[2 * i + 1]);
+      const float2 d2 = make_float2(d[2 * i], d[2 * i + 1]);
+      float2 cdf, pdf;
+      gelu_cdf_pdf2(g2, cdf, pdf);
+      const float2 du = __fmul2_rn(__fmul2_rn(d2, g2), cdf);
+      const float2 dg = __fmul2_rn(__fmul2_rn(d2, u2), __ffma2_rn(g2, pdf, cdf));
+      u[2 * i] = du.x; u[2 * i + 1] = du.y;
+      g[2 * i] = dg.x; g[2 * i + 1] = dg.y;
+    }
   }
   store8(dh + row * 2 * hd + hc, u);
   store8(dh + row * 2 * hd + hc + 32, g);
@@ -326,17 +340,31 @@ __global__ void __launch_bounds__(256) geglu_bwd_colsum_kernel(const T* __restri
     load8(h + (size_t)row * 2 * hd + hc, u);
     load8(h + (size_t)row * 2 * hd + hc + 32, g);
     load8(dout + (size_t)row * hd + oc, d);
+    if (sizeof(T) == 4) {                     // exact path
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float cdf = 0.5f * (1.0f + erff(g[i] * 0.70710678118654752f));
-      const float pdf = 0.39894228040143268f * expf(-0.5f * g[i] * g[i]);
-      const float du = d[i] * g[i] * cdf;
-      const float dg = d[i] * u[i] * fmaf(g[i], pdf, cdf);
-      u[i] = du;
-      g[i] = dg;
-      su[i] += du;
-      sg[i] += dg;
+      for (int i = 0; i < 8; ++i) {
+        const float cdf = 0.5f * (1.0f + erff(g[i] * 0.70710678118654752f));
+        const float pdf = 0.39894228040143268f * expf(-0.5f * g[i] * g[i]);
+        const float du = d[i] * g[i] * cdf;
+        const float dg = d[i] * u[i] * fmaf(g[i], pdf, cdf);
+        u[i] = du;
+        g[i] = dg;
+      }
+    } else {                                  // bf16 path: packed math (same arithmetic as geglu_bwd_kernel<bf16>)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 g2 = make_float2(g[2 * i], g[2 * i + 1]), u2 = make_float2(u[2 * i], u[2 * i + 1]);
+        const float2 d2 = make_float2(d[2 * i], d[2 * i + 1]);
+        float2 cdf, pdf;
+        gelu_cdf_pdf2(g2, cdf, pdf);
+        const float2 du = __fmul2_rn(__fmul2_rn(d2, g2), cdf);
+        const float2 dg = __fmul2_rn(__fmul2_rn(d2, u2), __ffma2_rn(g2, pdf, cdf));
+        u[2 * i] = du.x; u[2 * i + 1] = du.y;
+        g[2 * i] = dg.x; g[2 * i + 1] = dg.y;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { su[i] += u[i]; sg[i] += g[i]; }
     store8(dh + (size_t)row * 2 * hd + hc, u);
     store8(dh + (size_t)row * 2 * hd + hc + 32, g);
   }
