@@ -135,3 +135,30 @@ def test_xception_into_timesformer_matches_reference(prec):
         assert np.abs(logits.float().cpu().numpy() - g["logits"]).max() <= 2e-2
         assert rel_err(space.float().cpu(), g["space_attn"]) <= 2e-2
         assert rel_err(time.float().cpu(), g["time_attn"]) <= 2e-2
+
+
+def test_pack_xception_folds_batchnorm_and_orders_im2col_columns():
+    """host logic (CPU): the packed conv1 rows -- BatchNorm folded, columns (ky, kx, ci), 27 padded to 32 -- reproduce
+    bn1(conv1(x)) of the reference on an im2col matrix built the way xc_im2col3x3_kernel builds it; the first separable unit's
+    pointwise rows reproduce bn(pointwise(.))"""
+    import torch.nn.functional as F
+    from mintime_b200 import weights
+    sd = synth.make_xception_state_dict(2468)
+    pk = weights.pack_xception(sd, "fp32", "cpu")
+    w1, s1 = pk.keep[0], pk.keep[1]                                  # conv1: [32][32], shift [32]
+    assert tuple(w1.shape) == (32, 32) and float(w1[:, 27:].abs().max()) == 0.0
+    x = torch.rand((1, 3, 9, 9), generator=torch.Generator().manual_seed(1)) * 255.0
+    ref = xo._bn(sd, "bn1", F.conv2d(x, sd["conv1.weight"], None, 2, 0))           # (1,32,4,4)
+    cols = F.unfold(x, 3, stride=2)                                  # (1, ci*9, 16), rows ordered (ci, ky, kx)
+    cols = cols.view(1, 3, 9, 16).permute(0, 3, 2, 1).reshape(16, 27)  # -> [pixel][(ky,kx), ci]
+    cols = torch.cat([cols, torch.zeros(16, 5)], dim=1)
+    got = (cols @ w1.t() + s1).t().reshape(1, 32, 4, 4)
+    assert rel_err(got, ref) <= 1e-5
+    # unit 0 = block1.rep.0: keep[4] depthwise taps [9][64], keep[5] folded pointwise [128][64], keep[6] shift
+    dw, pw, sh = pk.keep[4], pk.keep[5], pk.keep[6]
+    assert tuple(dw.shape) == (9, 64) and tuple(pw.shape) == (128, 64)
+    a = torch.randn((1, 64, 5, 5), generator=torch.Generator().manual_seed(2))
+    ref = xo._bn(sd, "block1.rep.1", xo._sep(sd, "block1.rep.0", a))
+    mid = F.conv2d(a, dw.t().reshape(64, 1, 3, 3), None, 1, 1, 1, 64)
+    got = F.conv2d(mid, pw.reshape(128, 64, 1, 1)) + sh.view(1, -1, 1, 1)
+    assert rel_err(got, ref) <= 1e-5
